@@ -1,0 +1,459 @@
+// HP-1: pairwise coarse matcher (LoFTR coarse_only path) on the B200 -- layer schedule and C ABI.
+// Reference: third_party/LoFTR/src/loftr/loftr.py:29-73 (stage order), backbone/resnet_fpn.py:100-108 (coarse sub-graph),
+// loftr_module/transformer.py:35-101, utils/coarse_matching.py:84-258.
+#include <map>
+#include <memory>
+
+#include "../../include/dfsfm_b200.h"
+#include "engine_common.h"
+
+namespace dfsfm {
+
+namespace {
+
+struct Geom {
+    int H, W, Hp, Wp;
+    long long rows;  // per image
+    Geom() : H(0), W(0), Hp(0), Wp(0), rows(0) {}
+    Geom(int h, int w) : H(h), W(w), Hp(h + 1), Wp(w + 1), rows(static_cast<long long>(h + 1) * (w + 1)) {}
+    FlatGeom flat() const { return FlatGeom{Hp, Wp, H, W}; }
+};
+
+struct ParityBuf {  // [4 parity][2 hl][rows][C]
+    __half* base = nullptr;
+    long long rows = 0;
+    int C = 0;
+    HL plane(int k) const {
+        HL b;
+        b.hi = base + static_cast<long long>(k) * 2 * rows * C;
+        b.rows = rows;
+        b.C = C;
+        return b;
+    }
+    long long plane_stride() const { return 2 * rows * C; }
+};
+
+struct FeatWs {  // backbone workspace for one image geometry
+    Geom g2, g4, g8;
+    HL a2, b2, c2;
+    ParityBuf p1, p2;
+    HL a4, b4, a8, b8, c8;
+};
+
+struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per side
+    int cap = 0;
+    HL x[2], msg[2], m1[2], hid[2];
+    float* qkv[2] = {nullptr, nullptr};
+    float* kv_part = nullptr;
+    float* kv_state = nullptr;
+    Seg* seg_dev = nullptr;
+    float2* part = nullptr;
+    float2* stat[2] = {nullptr, nullptr};
+    unsigned long long* best[2] = {nullptr, nullptr};
+};
+
+}  // namespace
+
+class CoarseEngine {
+  public:
+    explicit CoarseEngine(int device) : device_(device) { DFSFM_CUDA(cudaSetDevice(device)); }
+    ~CoarseEngine() {
+        for (auto& kv : feat_ws_) free_feat(kv.second);
+        free_tok(tok_);
+    }
+    ParamStore params;
+
+    void features(const float* img, int H, int W, const float* pe, float* tokens, cudaStream_t st);
+    void transformer(float* f0, int L, float* f1, int S, cudaStream_t st);
+    void match(const float* f0, int h0c, int w0c, const float* f1, int h1c, int w1c, float thr, int border, float temperature, int* i_ids,
+               int* j_ids, float* mconf, int* n_matches, int capacity, float* conf_out, cudaStream_t st);
+
+  private:
+    int device_;
+    std::map<std::pair<int, int>, FeatWs> feat_ws_;
+    TokWs tok_;
+
+    FeatWs& get_feat_ws(int H, int W);
+    void ensure_tok(int n);
+    static void free_feat(FeatWs& w);
+    static void free_tok(TokWs& w);
+
+    template <int BN>
+    void conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st);
+    void layer_call(int li, bool self, int a, int na, int b, int nb, float* xa, cudaStream_t st);
+    void kv_state(int side, int n, cudaStream_t st);
+};
+
+static ParityBuf parity_alloc(long long rows, int C) {
+    ParityBuf p;
+    p.rows = rows;
+    p.C = C;
+    const size_t bytes = static_cast<size_t>(8) * rows * C * sizeof(__half);
+    DFSFM_CUDA(cudaMalloc(&p.base, bytes));
+    DFSFM_CUDA(cudaMemset(p.base, 0, bytes));
+    return p;
+}
+
+FeatWs& CoarseEngine::get_feat_ws(int H, int W) {
+    auto key = std::make_pair(H, W);
+    auto it = feat_ws_.find(key);
+    if (it != feat_ws_.end()) return it->second;
+    if (feat_ws_.size() >= 8) {  // bound the cache: drop everything (geometries repeat within a scene)
+        for (auto& kv : feat_ws_) free_feat(kv.second);
+        feat_ws_.clear();
+    }
+    FeatWs w;
+    w.g2 = Geom(H / 2, W / 2);
+    w.g4 = Geom(H / 4, W / 4);
+    w.g8 = Geom(H / 8, W / 8);
+    w.a2 = hl_alloc(w.g2.rows, 128);
+    w.b2 = hl_alloc(w.g2.rows, 128);
+    w.c2 = hl_alloc(w.g2.rows, 128);
+    w.p1 = parity_alloc(w.g4.rows, 128);
+    w.a4 = hl_alloc(w.g4.rows, 208);
+    w.b4 = hl_alloc(w.g4.rows, 208);
+    w.p2 = parity_alloc(w.g8.rows, 208);
+    w.a8 = hl_alloc(w.g8.rows, 256);
+    w.b8 = hl_alloc(w.g8.rows, 256);
+    w.c8 = hl_alloc(w.g8.rows, 256);
+    return feat_ws_.emplace(key, w).first->second;
+}
+void CoarseEngine::free_feat(FeatWs& w) {
+    hl_free(w.a2); hl_free(w.b2); hl_free(w.c2); hl_free(w.a4); hl_free(w.b4); hl_free(w.a8); hl_free(w.b8); hl_free(w.c8);
+    if (w.p1.base) cudaFree(w.p1.base);
+    if (w.p2.base) cudaFree(w.p2.base);
+}
+
+template <int BN>
+void CoarseEngine::conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st) {
+    const HL& w = params.mat(wname + ".w");
+    TmapPack maps;
+    for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(ins[i < n_in ? i : 0], kBM);
+    maps.b = make_tmap(w, BN);
+    core.b_row0 = 0;
+    DFSFM_CHECK(static_cast<long long>(core.num_taps) * core.cpad == w.C, "weight K does not match taps*cpad for " + wname);
+    ep.M = core.M;
+    ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
+    launch_gemm_counted<BN, true, ConvEpi>(maps, core, ep, ep.N, st);
+}
+
+static ConvEpiParams epi_flat(const Geom& g, int N, const HL& out, bool relu, const HL* res) {
+    ConvEpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.N = N;
+    e.g = g.flat();
+    e.relu = relu ? 1 : 0;
+    if (res) { e.res_hi = res->hi; e.res_lo = res->lo(); e.res_ld = res->C; }
+    e.out_mode = OUT_FLAT;
+    e.out_hi = out.hi;
+    e.out_lo = out.lo();
+    e.out_ld = out.C;
+    return e;
+}
+static ConvEpiParams epi_parity(const Geom& g, int N, const ParityBuf& out, bool relu, const HL* res) {
+    ConvEpiParams e = epi_flat(g, N, out.plane(0), relu, res);
+    e.out_mode = OUT_PARITY;
+    e.plane_stride = out.plane_stride();
+    return e;
+}
+
+void CoarseEngine::features(const float* img, int H, int W, const float* pe, float* tokens, cudaStream_t st) {
+    DFSFM_CHECK(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "image size must be a multiple of 8 (CoarseMatchingDataset df=8)");
+    FeatWs& w = get_feat_ws(H, W);
+    // conv1 + bn1 + relu (resnet_fpn.py:102)
+    {
+        dim3 grid((w.g2.W + kStemTW - 1) / kStemTW, (w.g2.H + kStemTH - 1) / kStemTH, 1);
+        stem_conv_kernel<<<grid, 128, 0, st>>>(img, H, W, params.vec("stem.w"), params.vec("stem.b"), w.a2.hi, w.a2.lo());
+        count_launch();
+        DFSFM_CUDA(cudaGetLastError());
+    }
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    // layer1 (two BasicBlocks, stride 1, 128 ch) -- resnet_fpn.py:32-40,103
+    c.M = static_cast<int>(w.g2.rows);
+    set_k(c, 128);
+    conv_taps_s1(c, 3, w.g2.Wp);
+    { const HL in[1] = {w.a2}; conv<128>(in, 1, c, "l1.0.c1", epi_flat(w.g2, 128, w.b2, true, nullptr), st); }
+    { const HL in[1] = {w.b2}; conv<128>(in, 1, c, "l1.0.c2", epi_flat(w.g2, 128, w.c2, true, &w.a2), st); }
+    { const HL in[1] = {w.c2}; conv<128>(in, 1, c, "l1.1.c1", epi_flat(w.g2, 128, w.b2, true, nullptr), st); }
+    { const HL in[1] = {w.b2}; conv<128>(in, 1, c, "l1.1.c2", epi_parity(w.g2, 128, w.p1, true, &w.c2), st); }
+    // layer2 (stride 2, 196 -> 208 padded channels) -- the 1x1 stride-2 downsample rides as a 10th tap of conv2
+    c.M = static_cast<int>(w.g4.rows);
+    set_k(c, 128);
+    conv_taps_s2(c, w.g4.Wp);
+    { const HL in[4] = {w.p1.plane(0), w.p1.plane(1), w.p1.plane(2), w.p1.plane(3)};
+      conv<208>(in, 4, c, "l2.0.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
+    set_k(c, 208);
+    conv_taps_s1(c, 3, w.g4.Wp);
+    c.num_taps = 10; c.tap_map[9] = 1; c.tap_shift[9] = 0;
+    { const HL in[2] = {w.a4, w.p1.plane(0)}; conv<208>(in, 2, c, "l2.0.c2", epi_flat(w.g4, 208, w.b4, true, nullptr), st); }
+    conv_taps_s1(c, 3, w.g4.Wp);
+    { const HL in[1] = {w.b4}; conv<208>(in, 1, c, "l2.1.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
+    { const HL in[1] = {w.a4}; conv<208>(in, 1, c, "l2.1.c2", epi_parity(w.g4, 208, w.p2, true, &w.b4), st); }
+    // layer3 (stride 2, 256 ch)
+    c.M = static_cast<int>(w.g8.rows);
+    set_k(c, 208);
+    conv_taps_s2(c, w.g8.Wp);
+    { const HL in[4] = {w.p2.plane(0), w.p2.plane(1), w.p2.plane(2), w.p2.plane(3)};
+      conv<256>(in, 4, c, "l3.0.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
+    set_k(c, 256);
+    conv_taps_s1(c, 3, w.g8.Wp);
+    c.num_taps = 10; c.tap_map[9] = 1; c.tap_shift[9] = 0;
+    { const HL in[2] = {w.a8, w.p2.plane(0)}; conv<256>(in, 2, c, "l3.0.c2", epi_flat(w.g8, 256, w.b8, true, nullptr), st); }
+    conv_taps_s1(c, 3, w.g8.Wp);
+    { const HL in[1] = {w.b8}; conv<256>(in, 1, c, "l3.1.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
+    { const HL in[1] = {w.a8}; conv<256>(in, 1, c, "l3.1.c2", epi_flat(w.g8, 256, w.c8, true, &w.b8), st); }
+    // layer3_outconv (1x1) + position encoding + flatten to tokens (resnet_fpn.py:108, loftr.py:58)
+    conv_taps_s1(c, 1, w.g8.Wp);
+    {
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.N = 256;
+        e.g = w.g8.flat();
+        e.addend = pe;
+        e.out_mode = OUT_DENSE;
+        e.out_f32 = tokens;
+        e.out_f32_ld = 256;
+        const HL in[1] = {w.c8};
+        conv<256>(in, 1, c, "out3", e, st);
+    }
+}
+
+// -------------------------------------------------------------------------------------------- transformer
+void CoarseEngine::free_tok(TokWs& w) {
+    for (int s = 0; s < 2; ++s) {
+        hl_free(w.x[s]); hl_free(w.msg[s]); hl_free(w.m1[s]); hl_free(w.hid[s]);
+        if (w.qkv[s]) cudaFree(w.qkv[s]);
+        if (w.stat[s]) cudaFree(w.stat[s]);
+        if (w.best[s]) cudaFree(w.best[s]);
+        w.qkv[s] = nullptr; w.stat[s] = nullptr; w.best[s] = nullptr;
+    }
+    if (w.kv_part) cudaFree(w.kv_part);
+    if (w.kv_state) cudaFree(w.kv_state);
+    if (w.seg_dev) cudaFree(w.seg_dev);
+    if (w.part) cudaFree(w.part);
+    w.kv_part = w.kv_state = nullptr; w.seg_dev = nullptr; w.part = nullptr;
+    w.cap = 0;
+}
+void CoarseEngine::ensure_tok(int n) {
+    if (n <= tok_.cap) return;
+    free_tok(tok_);
+    const int cap = ((n + 1023) / 1024) * 1024;
+    tok_.cap = cap;
+    for (int s = 0; s < 2; ++s) {
+        tok_.x[s] = hl_alloc(cap, 256);
+        tok_.msg[s] = hl_alloc(cap, 256);
+        tok_.m1[s] = hl_alloc(cap, 256);
+        tok_.hid[s] = hl_alloc(cap, 512);
+        DFSFM_CUDA(cudaMalloc(&tok_.qkv[s], static_cast<size_t>(cap) * 768 * sizeof(float)));
+        DFSFM_CUDA(cudaMalloc(&tok_.stat[s], static_cast<size_t>(cap) * sizeof(float2)));
+        DFSFM_CUDA(cudaMalloc(&tok_.best[s], static_cast<size_t>(cap) * sizeof(unsigned long long)));
+    }
+    const int chunks = (cap + kKvTokPerCta - 1) / kKvTokPerCta;
+    DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(chunks) * 256 * 33 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(256) * 33 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 2 * sizeof(Seg)));
+    const int tiles = (cap + 255) / 256;
+    DFSFM_CUDA(cudaMalloc(&tok_.part, static_cast<size_t>(tiles) * cap * sizeof(float2)));
+}
+
+// KV state of side `side` (n tokens): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
+void CoarseEngine::kv_state(int side, int n, cudaStream_t st) {
+    const int chunks = (n + kKvTokPerCta - 1) / kKvTokPerCta;
+    kv_partial_kernel<32><<<dim3(chunks, 1), 256, 0, st>>>(tok_.qkv[side] + 256, tok_.qkv[side] + 512, 768, tok_.seg_dev + side, chunks,
+                                                            tok_.kv_part);
+    count_launch();
+    kv_final_kernel<32><<<1, 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + side, chunks, tok_.kv_state);
+    count_launch();
+    DFSFM_CUDA(cudaGetLastError());
+}
+
+// One LoFTREncoderLayer.forward(x = side a, source = side b)  (transformer.py:35-58); xa = fp32 tokens of side a (updated in place).
+void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, float* xa, cudaStream_t st) {
+    const std::string p = "tr." + std::to_string(li);
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    set_k(c, 256);
+    conv_taps_s1(c, 1, 0);
+    LinEpiParams e;
+    // q/k/v projections (+ elu+1 feature map on q,k)
+    {
+        TmapPack maps;
+        const HL& wq = params.mat(p + ".qkv");
+        maps.b = make_tmap(wq, 256);
+        memset(&e, 0, sizeof(e));
+        e.mode = LIN_F32_ELU;
+        e.out_f32_ld = 768;
+        if (self) {
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
+            c.M = na; c.b_row0 = 0;
+            e.M = na; e.N = 768; e.elu_cols = 512; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st);
+        } else {
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
+            c.M = na; c.b_row0 = 0;
+            e.M = na; e.N = 256; e.elu_cols = 256; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st);
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[b], kBM);
+            c.M = nb; c.b_row0 = 256;
+            e.M = nb; e.N = 512; e.elu_cols = 256; e.out_f32 = tok_.qkv[b]; e.out_col0 = 256;
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st);
+        }
+    }
+    kv_state(b, nb, st);
+    {
+        const int blocks = (na + 63) / 64;
+        attn_apply_kernel<32><<<dim3(blocks, 1), 256, 0, st>>>(tok_.qkv[a], 768, tok_.seg_dev + a, tok_.kv_state, tok_.msg[a].hi,
+                                                                tok_.msg[a].lo(), 256);
+        count_launch();
+        DFSFM_CUDA(cudaGetLastError());
+    }
+    // merge + norm1
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.msg[a], kBM);
+        maps.b = make_tmap(params.mat(p + ".merge"), 256);
+        c.M = na; c.b_row0 = 0;
+        memset(&e, 0, sizeof(e));
+        e.M = na; e.N = 256; e.mode = LIN_LN;
+        e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
+        e.out_hi = tok_.m1[a].hi; e.out_lo = tok_.m1[a].lo(); e.out_ld = 256;
+        launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st);
+    }
+    // mlp.0 on cat[x, message] + relu
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(i == 1 ? tok_.m1[a] : tok_.x[a], kBM);
+        maps.b = make_tmap(params.mat(p + ".mlp0"), 256);
+        GemmCore c2 = c;
+        c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
+        memset(&e, 0, sizeof(e));
+        e.M = na; e.N = 512; e.mode = LIN_RELU_HL;
+        e.out_hi = tok_.hid[a].hi; e.out_lo = tok_.hid[a].lo(); e.out_ld = 512;
+        launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st);
+    }
+    // mlp.2 + norm2 + residual
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.hid[a], kBM);
+        maps.b = make_tmap(params.mat(p + ".mlp2"), 256);
+        GemmCore c3 = c;
+        set_k(c3, 512);
+        memset(&e, 0, sizeof(e));
+        e.M = na; e.N = 256; e.mode = LIN_LN;
+        e.gamma = params.vec(p + ".ln2.g"); e.beta = params.vec(p + ".ln2.b");
+        e.resid = xa; e.resid_ld = 256;
+        e.out_f32 = xa; e.out_f32_ld = 256;
+        e.out_hi = tok_.x[a].hi; e.out_lo = tok_.x[a].lo(); e.out_ld = 256;
+        launch_gemm_counted<256, true, LinEpi>(maps, c3, e, 256, st);
+    }
+}
+
+static void split_rows(const float* in, long long rows, int C, const HL& out, cudaStream_t st) {
+    const long long n4 = rows * C / 4;
+    split_rows_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(in, n4, out.hi, out.lo());
+    count_launch();
+    DFSFM_CUDA(cudaGetLastError());
+}
+
+void CoarseEngine::transformer(float* f0, int L, float* f1, int S, cudaStream_t st) {
+    ensure_tok(L > S ? L : S);
+    const Seg segs[2] = {{0, L, L, 0}, {0, S, S, 0}};
+    DFSFM_CUDA(cudaMemcpyAsync(tok_.seg_dev, segs, sizeof(segs), cudaMemcpyHostToDevice, st));
+    // the token planes have a fixed capacity; rows beyond L/S are never read by valid output rows
+    split_rows(f0, L, 256, tok_.x[0], st);
+    split_rows(f1, S, 256, tok_.x[1], st);
+    for (int li = 0; li < 8; ++li) {
+        const bool self = (li % 2) == 0;  // layer_names = ['self','cross'] * 4 (default.py:22)
+        if (self) {
+            layer_call(li, true, 0, L, 0, L, f0, st);
+            layer_call(li, true, 1, S, 1, S, f1, st);
+        } else {
+            layer_call(li, false, 0, L, 1, S, f0, st);  // feat0 attends feat1
+            layer_call(li, false, 1, S, 0, L, f1, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ matching
+void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int h1c, int w1c, float thr, int border, float temperature,
+                         int* i_ids, int* j_ids, float* mconf, int* n_matches, int capacity, float* conf_out, cudaStream_t st) {
+    const int L = h0c * w0c, S = h1c * w1c;
+    ensure_tok(L > S ? L : S);
+    split_rows(f0, L, 256, tok_.x[0], st);
+    split_rows(f1, S, 256, tok_.x[1], st);
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    set_k(c, 256);
+    conv_taps_s1(c, 1, 0);
+    SimEpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.scale = 1.f / 256.f;  // (f0 / sqrt(256)) . (f1 / sqrt(256))   (coarse_matching.py:103-104)
+    e.temperature = temperature;
+    const int n[2] = {L, S};
+    // softmax statistics along both axes: rows of sim (dim=2) and rows of sim^T (dim=1)
+    for (int side = 0; side < 2; ++side) {
+        const int o = 1 - side;
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[side].hi, 256, n[side], tok_.x[side].plane_elems(), kBM);
+        maps.b = make_tmap(tok_.x[o].hi, 256, n[o], tok_.x[o].plane_elems(), 256);
+        c.M = n[side];
+        e.M = n[side]; e.N = n[o]; e.mode = SIM_STATS; e.part = tok_.part;
+        launch_gemm_counted<256, true, SimEpi>(maps, c, e, n[o], st);
+        const int tiles = (n[o] + 255) / 256;
+        stats_merge_kernel<<<(n[side] + 255) / 256, 256, 0, st>>>(tok_.part, tiles, n[side], tok_.stat[side]);
+        count_launch();
+    }
+    DFSFM_CUDA(cudaMemsetAsync(tok_.best[0], 0, static_cast<size_t>(L) * 8, st));
+    DFSFM_CUDA(cudaMemsetAsync(tok_.best[1], 0, static_cast<size_t>(S) * 8, st));
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[0].hi, 256, L, tok_.x[0].plane_elems(), kBM);
+        maps.b = make_tmap(tok_.x[1].hi, 256, S, tok_.x[1].plane_elems(), 256);
+        c.M = L;
+        e.M = L; e.N = S; e.mode = SIM_CONF;
+        e.row_stat = tok_.stat[0]; e.col_stat = tok_.stat[1]; e.thr = thr;
+        e.row_best = tok_.best[0]; e.col_best = tok_.best[1]; e.conf_out = conf_out;
+        launch_gemm_counted<256, true, SimEpi>(maps, c, e, S, st);
+    }
+    match_select_kernel<<<1, 1024, 0, st>>>(tok_.best[0], tok_.best[1], L, w0c, w1c, border, capacity, i_ids, j_ids, mconf, n_matches);
+    count_launch();
+    DFSFM_CUDA(cudaGetLastError());
+}
+
+}  // namespace dfsfm
+
+// ================================================================================================ C ABI
+using dfsfm::CoarseEngine;
+struct dfsfm_coarse { std::unique_ptr<CoarseEngine> e; };
+
+extern "C" {
+
+int dfsfm_coarse_create(dfsfm_coarse_t** out, int device) {
+    return dfsfm::guard([&] {
+        auto* h = new dfsfm_coarse;
+        h->e.reset(new CoarseEngine(device));
+        *out = h;
+    });
+}
+void dfsfm_coarse_destroy(dfsfm_coarse_t* h) { delete h; }
+
+int dfsfm_coarse_set_param(dfsfm_coarse_t* h, const char* name, const float* host, int64_t rows, int64_t cols, int kind) {
+    return dfsfm::guard([&] { h->e->params.set(name, host, rows, cols, kind); });
+}
+int dfsfm_coarse_features(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev, void* stream) {
+    return dfsfm::guard([&] { h->e->features(image_dev, H, W, pe_dev, tokens_out_dev, static_cast<cudaStream_t>(stream)); });
+}
+int dfsfm_coarse_transformer(dfsfm_coarse_t* h, float* feat0_dev, int L, float* feat1_dev, int S, void* stream) {
+    return dfsfm::guard([&] { h->e->transformer(feat0_dev, L, feat1_dev, S, static_cast<cudaStream_t>(stream)); });
+}
+int dfsfm_coarse_match(dfsfm_coarse_t* h, const float* feat0_dev, int h0c, int w0c, const float* feat1_dev, int h1c, int w1c, float thr,
+                       int border_rm, float temperature, int32_t* i_ids_dev, int32_t* j_ids_dev, float* mconf_dev, int32_t* n_matches_dev,
+                       int capacity, float* conf_out_dev, void* stream) {
+    return dfsfm::guard([&] {
+        h->e->match(feat0_dev, h0c, w0c, feat1_dev, h1c, w1c, thr, border_rm, temperature, i_ids_dev, j_ids_dev, mconf_dev, n_matches_dev,
+                    capacity, conf_out_dev, static_cast<cudaStream_t>(stream));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// Library-wide state (last error, launch counter), the standalone RoIAlign op and the engine test hook.
+#include "../../include/dfsfm_b200.h"
+#include "engine_common.h"
+
+namespace dfsfm {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> c{0};
+    return c;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TensorFlow-style crop_and_resize forward (the reference's L0 native op):
+//   third_party/RoIAlign.pytorch/roi_align/src/cuda/crop_and_resize_kernel.cu:10-82 (semantics),
+//   roi_align/src/crop_and_resize.cpp:7-113 (CPU twin the oracle is checked against).
+// One CTA per (box, channel-group); the needed source rows are read with coalesced row segments, every output
+// element costs 4 cached loads and 3 lerps, outputs are written fully coalesced (NCHW rows of crop_w floats).
+__global__ void __launch_bounds__(256) crop_and_resize_kernel(const float* __restrict__ image, int batch, int depth, int ih, int iw,
+                                                              const float* __restrict__ boxes, const int* __restrict__ box_index,
+                                                              float extrapolation, int ch, int cw, float* __restrict__ crops) {
+    const int b = blockIdx.x;
+    const float y1 = boxes[b * 4 + 0], x1 = boxes[b * 4 + 1], y2 = boxes[b * 4 + 2], x2 = boxes[b * 4 + 3];
+    const int b_in = box_index[b];
+    const long long crop_elems = static_cast<long long>(depth) * ch * cw;
+    float* out = crops + b * crop_elems;
+    if (b_in < 0 || b_in >= batch) {  // the reference silently skips such boxes on the GPU (kernel.cu:36-39)
+        return;
+    }
+    const float height_scale = (ch > 1) ? (y2 - y1) * (ih - 1) / (ch - 1) : 0.f;
+    const float width_scale = (cw > 1) ? (x2 - x1) * (iw - 1) / (cw - 1) : 0.f;
+    const float* img = image + static_cast<long long>(b_in) * depth * ih * iw;
+    for (long long idx = threadIdx.x; idx < crop_elems; idx += blockDim.x) {
+        const int x = static_cast<int>(idx % cw);
+        const int y = static_cast<int>((idx / cw) % ch);
+        const int d = static_cast<int>(idx / (static_cast<long long>(cw) * ch));
+        const float in_y = (ch > 1) ? y1 * (ih - 1) + y * height_scale : 0.5f * (y1 + y2) * (ih - 1);
+        const float in_x = (cw > 1) ? x1 * (iw - 1) + x * width_scale : 0.5f * (x1 + x2) * (iw - 1);
+        float v = extrapolation;
+        if (!(in_y < 0 || in_y > ih - 1 || in_x < 0 || in_x > iw - 1)) {
+            const int top = static_cast<int>(floorf(in_y)), bottom = static_cast<int>(ceilf(in_y));
+            const int left = static_cast<int>(floorf(in_x)), right = static_cast<int>(ceilf(in_x));
+            const float y_lerp = in_y - top, x_lerp = in_x - left;
+            const float* p = img + static_cast<long long>(d) * ih * iw;
+            const float tl = __ldg(p + static_cast<long long>(top) * iw + left);
+            const float tr = __ldg(p + static_cast<long long>(top) * iw + right);
+            const float bl = __ldg(p + static_cast<long long>(bottom) * iw + left);
+            const float br = __ldg(p + static_cast<long long>(bottom) * iw + right);
+            const float t = tl + (tr - tl) * x_lerp;
+            const float bt = bl + (br - bl) * x_lerp;
+            v = t + (bt - t) * y_lerp;
+        }
+        out[idx] = v;
+    }
+}
+
+}  // namespace dfsfm
+
+extern "C" {
+
+const char* dfsfm_last_error(void) { return dfsfm::g_last_error.c_str(); }
+int dfsfm_version(void) { return 1; }
+int64_t dfsfm_launch_count(void) { return dfsfm::launch_counter().load(); }
+
+int dfsfm_crop_and_resize_forward(const float* image_dev, int batch, int depth, int image_h, int image_w, const float* boxes_dev,
+                                  const int32_t* box_index_dev, int num_boxes, float extrapolation_value, int crop_h, int crop_w,
+                                  float* crops_dev, void* stream) {
+    return dfsfm::guard([&] {
+        if (num_boxes <= 0) return;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        // crops.zero_() of the reference (crop_and_resize_gpu.cpp:42-43): boxes with an invalid index keep zeros
+        DFSFM_CUDA(cudaMemsetAsync(crops_dev, 0, static_cast<size_t>(num_boxes) * depth * crop_h * crop_w * sizeof(float), st));
+        dfsfm::crop_and_resize_kernel<<<num_boxes, 256, 0, st>>>(image_dev, batch, depth, image_h, image_w, boxes_dev, box_index_dev,
+                                                                extrapolation_value, crop_h, crop_w, crops_dev);
+        dfsfm::count_launch();
+        DFSFM_CUDA(cudaGetLastError());
+    });
+}
+
+int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts, int cpad,
+                     int bn, int split, float* out_dev, int M, int N, void* stream) {
+    using namespace dfsfm;
+    return guard([&] {
+        DFSFM_CHECK(taps >= 1 && taps <= kMaxTaps, "taps out of range");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const __half* a = static_cast<const __half*>(a_dev);
+        const __half* w = static_cast<const __half*>(w_dev);
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(a, C, a_rows, a_rows * C, kBM);
+        const long long ktot = static_cast<long long>(taps) * cpad;
+        maps.b = make_tmap(w, static_cast<int>(ktot), w_rows, w_rows * ktot, bn);
+        GemmCore c;
+        memset(&c, 0, sizeof(c));
+        c.M = M;
+        c.num_taps = taps;
+        set_k(c, cpad);
+        for (int t = 0; t < taps; ++t) { c.tap_map[t] = 0; c.tap_shift[t] = shifts[t]; }
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.M = M; e.N = N; e.out_mode = OUT_FLAT; e.out_f32 = out_dev; e.out_f32_ld = N;
+#define DFSFM_CASE(BN_)                                                                  \
+    if (bn == BN_) {                                                                     \
+        if (split) launch_gemm_counted<BN_, true, ConvEpi>(maps, c, e, N, st);           \
+        else launch_gemm_counted<BN_, false, ConvEpi>(maps, c, e, N, st);                \
+        return;                                                                          \
+    }
+        DFSFM_CASE(64) DFSFM_CASE(128) DFSFM_CASE(208) DFSFM_CASE(256)
+#undef DFSFM_CASE
+        throw Error("unsupported bn");
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Shared by the engine translation units: parameter store, C-ABI error guard, launch counter.
+#pragma once
+#include <atomic>
+#include <functional>
+#include <map>
+#include <string>
+
+#include "host_utils.h"
+#include "simt_kernels.cuh"
+
+namespace dfsfm {
+
+void set_last_error(const std::string& s);
+std::atomic<long long>& launch_counter();
+inline void count_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
+
+template <class F>
+inline int guard(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return 1;
+    } catch (...) {
+        set_last_error("unknown error");
+        return 2;
+    }
+}
+
+template <int BN, bool kSplit, class Epi>
+inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
+    launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+    count_launch();
+}
+
+// Packed parameters on the device: GEMM operands as split-fp16 [rows][cols], everything else as fp32.
+class ParamStore {
+  public:
+    ~ParamStore() {
+        for (auto& kv : mats_) hl_free(kv.second);
+        for (auto& kv : vecs_) cudaFree(kv.second);
+    }
+    void set(const std::string& name, const float* host, long long rows, long long cols, int kind) {
+        const long long n = rows * cols;
+        DFSFM_CHECK(n > 0, "empty parameter " + name);
+        if (kind == 0) {
+            DFSFM_CHECK(cols % 8 == 0, "GEMM operand K must be a multiple of 8: " + name);
+            std::vector<__half> tmp(static_cast<size_t>(2 * n));
+            for (long long i = 0; i < n; ++i) {
+                const __half h = __float2half_rn(host[i]);
+                tmp[i] = h;
+                tmp[n + i] = __float2half_rn(host[i] - __half2float(h));
+            }
+            auto it = mats_.find(name);
+            if (it != mats_.end()) { hl_free(it->second); mats_.erase(it); }
+            HL b = hl_alloc(rows, static_cast<int>(cols));
+            DFSFM_CUDA(cudaMemcpy(b.hi, tmp.data(), tmp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            mats_[name] = b;
+        } else {
+            auto it = vecs_.find(name);
+            if (it != vecs_.end()) { cudaFree(it->second); vecs_.erase(it); }
+            float* d = nullptr;
+            DFSFM_CUDA(cudaMalloc(&d, static_cast<size_t>(n) * sizeof(float)));
+            DFSFM_CUDA(cudaMemcpy(d, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice));
+            vecs_[name] = d;
+        }
+    }
+    const HL& mat(const std::string& name) const {
+        auto it = mats_.find(name);
+        if (it == mats_.end()) throw Error("missing GEMM parameter '" + name + "' (upload weights first)");
+        return it->second;
+    }
+    const float* vec(const std::string& name) const {
+        auto it = vecs_.find(name);
+        if (it == vecs_.end()) throw Error("missing fp32 parameter '" + name + "' (upload weights first)");
+        return it->second;
+    }
+    bool has_vec(const std::string& name) const { return vecs_.count(name) != 0; }
+
+  private:
+    std::map<std::string, HL> mats_;
+    std::map<std::string, float*> vecs_;
+};
+
+}  // namespace dfsfm

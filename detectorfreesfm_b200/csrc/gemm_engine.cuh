@@ -1,0 +1,491 @@
+// Shifted-row implicit-GEMM engine on tcgen05 tensor cores (sm_100a).
+//
+//   acc[p, n] = sum_t sum_c  A_t[p + shift_t, c] * Wt[n, t*cpad + c]          (fp32 accumulate in TMEM)
+//
+// One kernel serves every dense contraction of both hot paths:
+//   * 3x3 / 5x5 / 1x1 convolutions on "flat halo" NHWC activations (a conv tap is a pure row shift),
+//   * stride-2 convolutions (taps read the four parity planes written by the previous layer's epilogue),
+//   * linear layers (one tap, shift 0; a concat of two inputs is two taps),
+//   * the LxS similarity GEMM of the dual-softmax matcher.
+// Operands are "split-fp16": every fp32 value x is stored as two fp16 planes (hi, lo) with hi+lo ~= x to 22 bits, and a
+// K-step issues hi*hi + hi*lo + lo*hi (3 tcgen05.mma, kind::f16) -- fp32-grade results at tensor-core rate (kSplit=true),
+// or a single hi*hi pass (kSplit=false).
+//
+// CTA = 128 x BN output tile, 192 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocator),
+// warps 2..5 = epilogue (TMEM -> registers -> global).  A/B tiles are [rows][64 halves] with the 128-byte TMA swizzle.
+#pragma once
+#include "tc_common.cuh"
+
+namespace dfsfm {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kMaxTaps = 26;
+constexpr int kMaxAMaps = 5;
+constexpr int kGemmThreads = 192;
+
+struct TmapPack {
+    CUtensorMap a[kMaxAMaps];  // activation planes: dims {C, rows, 2 (hi/lo)}, box {64, 128, 1}
+    CUtensorMap b;             // weights: dims {Ktot, Nrows, 2 (hi/lo)}, box {64, BN, 1}
+};
+
+struct GemmCore {
+    int M;         // rows of the flat index space
+    int num_taps;  // <= kMaxTaps
+    int kchunks;   // 64-wide K chunks per tap = ceil(cpad / 64)
+    int k16_last;  // valid 16-wide K steps in the last chunk of a tap (1..4)
+    int cpad;      // K elements per tap in the weight matrix
+    int b_row0;    // first weight row (output channel) of this launch
+    int8_t tap_map[kMaxTaps];  // which activation map a tap reads
+    int tap_shift[kMaxTaps];   // row shift of a tap
+};
+
+template <int BN, bool kSplit>
+struct GemmCfg {
+    static constexpr int kABytes = kBM * 128;  // one plane of an A tile
+    static constexpr int kBBytes = BN * 128;   // one plane of a B tile
+    static constexpr int kPlanes = kSplit ? 2 : 1;
+    static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+    static constexpr int kBudget = 200 * 1024;
+    static constexpr int kStagesRaw = kBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static_assert(kStages >= 2, "tile too large");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
+};
+
+// Epi must provide:  struct Params;  static __device__ void run(const Params&, uint32_t tmem_warp, int row0_warp, int lane, int n0)
+template <int BN, bool kSplit, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep) {
+    using Cfg = GemmCfg<BN, kSplit>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * kBM;
+    const int n0 = blockIdx.y * BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
+        tma_prefetch_desc(&maps.b);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_iters = core.num_taps * core.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int t = it / core.kchunks;
+                const int c = it - t * core.kchunks;
+                mbar_wait(&empty_bar[s], phase ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], Cfg::kStageBytes);
+                uint8_t* st = smem + s * Cfg::kStageBytes;
+                const CUtensorMap* am = &maps.a[core.tap_map[t]];
+                const int row = m0 + core.tap_shift[t];
+                const int kb = t * core.cpad + c * kBK;
+                tma_load_3d(st, am, &full_bar[s], c * kBK, row, 0);
+                if (kSplit) tma_load_3d(st + Cfg::kABytes, am, &full_bar[s], c * kBK, row, 1);
+                uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+                tma_load_3d(sb, &maps.b, &full_bar[s], kb, core.b_row0 + n0, 0);
+                if (kSplit) tma_load_3d(sb + Cfg::kBBytes, &maps.b, &full_bar[s], kb, core.b_row0 + n0, 1);
+                if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(kBM, BN);
+            int s = 0;
+            uint32_t phase = 0;
+            uint32_t acc = 0;
+            for (int it = 0; it < n_iters; ++it) {
+                const int c = it % core.kchunks;
+                mbar_wait(&full_bar[s], phase);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+                const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+                const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
+                for (int k = 0; k < nk; ++k) {
+                    const uint64_t da = make_smem_desc_sw128(a_hi + k * 32);
+                    const uint64_t db = make_smem_desc_sw128(b_hi + k * 32);
+                    umma_f16(tmem_base, da, db, idesc, acc);
+                    acc = 1;
+                    if (kSplit) {
+                        const uint64_t dal = make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32);
+                        const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + k * 32);
+                        umma_f16(tmem_base, da, dbl, idesc, 1);
+                        umma_f16(tmem_base, dal, db, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[s]);
+                if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full_bar);
+        }
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may read
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        Epi::template run<BN>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0);
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ epilogues
+// Geometry of a "flat halo" index space: image n, row y, col x  <->  p = n*Hp*Wp + y*Wp + x with Hp = H+1, Wp = W+1.
+// Column x == W and row y == H are zero halo cells shared by neighbouring rows / images: they are zeroed when the
+// buffer is allocated and never written afterwards, so a conv tap (dy,dx) is the row shift dy*Wp + dx.
+struct FlatGeom {
+    int Hp, Wp, H, W;  // Hp == 0: dense rows (no halo)
+};
+
+enum OutMode : int {
+    OUT_FLAT = 0,    // same flat geometry as the input index space
+    OUT_PARITY = 1,  // four half-resolution parity planes (feeds a stride-2 conv)
+    OUT_DENSE = 2,   // dense token rows n*H*W + y*W + x
+    OUT_WINDOW = 3,  // a (wh x ww) window at (y0,x0) re-packed into its own flat-halo geometry
+};
+
+struct ConvEpiParams {
+    int M, N;           // valid rows, output channels to write (padded channel count of the output buffer)
+    FlatGeom g;
+    const float* bias;  // [>= N] (BatchNorm folded), may be null
+    int relu;
+    const __half* res_hi;  // optional residual in the input flat geometry
+    const __half* res_lo;
+    int res_ld;
+    const float* addend;  // optional fp32 addend indexed [y*W + x][N] (position encoding)
+    int out_mode;
+    __half* out_hi;
+    __half* out_lo;
+    int out_ld;
+    long long plane_stride;  // OUT_PARITY: elements between consecutive parity planes
+    float* out_f32;          // optional fp32 copy (same row mapping as out_hi)
+    int out_f32_ld;
+    int wy0, wx0, wh, ww;    // OUT_WINDOW
+};
+
+struct ConvEpi {
+    using Params = ConvEpiParams;
+    template <int BN>
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+        const int row = row0 + lane;
+        bool valid = row < p.M;
+        int n_img = 0, y = 0, x = 0;
+        if (p.g.Hp > 0) {
+            const int per = p.g.Hp * p.g.Wp;
+            n_img = row / per;
+            const int r = row - n_img * per;
+            y = r / p.g.Wp;
+            x = r - y * p.g.Wp;
+            valid = valid && (y < p.g.H) && (x < p.g.W);
+        }
+        long long orow = row;   // output row index
+        long long obase = 0;    // extra element offset (parity plane)
+        if (p.out_mode == OUT_PARITY) {
+            const int Hp2 = p.g.H / 2 + 1, Wp2 = p.g.W / 2 + 1;
+            obase = static_cast<long long>((y & 1) * 2 + (x & 1)) * p.plane_stride;
+            orow = static_cast<long long>(n_img) * Hp2 * Wp2 + (y >> 1) * Wp2 + (x >> 1);
+        } else if (p.out_mode == OUT_DENSE) {
+            orow = static_cast<long long>(n_img) * p.g.H * p.g.W + y * p.g.W + x;
+        } else if (p.out_mode == OUT_WINDOW) {
+            valid = valid && y >= p.wy0 && y < p.wy0 + p.wh && x >= p.wx0 && x < p.wx0 + p.ww;
+            orow = static_cast<long long>(n_img) * (p.wh + 1) * (p.ww + 1) + (y - p.wy0) * (p.ww + 1) + (x - p.wx0);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_warp + c0, v);  // warp-collective: every lane executes it
+            tmem_ld_wait();
+            const int nb = n0 + c0;
+            if (!valid || nb >= p.N) continue;
+            const int ncnt = p.N - nb;  // columns to write in this chunk (a multiple of 8; may exceed 32)
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncnt) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb + j));
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                }
+            }
+            if (p.res_hi) {
+                const __half* rh = p.res_hi + static_cast<long long>(row) * p.res_ld + nb;
+                const __half* rl = p.res_lo + static_cast<long long>(row) * p.res_ld + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncnt) {
+                        const uint4 uh = *reinterpret_cast<const uint4*>(rh + j);
+                        const uint4 ul = *reinterpret_cast<const uint4*>(rl + j);
+                        const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+                        const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float2 a = __half22float2(hh[q]);
+                            const float2 b = __half22float2(hl[q]);
+                            v[j + 2 * q] += a.x + b.x;
+                            v[j + 2 * q + 1] += a.y + b.y;
+                        }
+                    }
+                }
+            }
+            if (p.addend) {
+                const float* ad = p.addend + static_cast<long long>(y * p.g.W + x) * p.N + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncnt) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(ad + j));
+                        v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+                    }
+                }
+            }
+            if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (p.out_hi) {
+                __half* oh = p.out_hi + obase + orow * p.out_ld + nb;
+                __half* ol = p.out_lo ? p.out_lo + obase + orow * p.out_ld + nb : nullptr;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    if (j < ncnt) {
+                        uint4 uh, ul;
+                        __half* hh = reinterpret_cast<__half*>(&uh);
+                        __half* hl = reinterpret_cast<__half*>(&ul);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) split_f16(v[j + q], hh[q], hl[q]);
+                        *reinterpret_cast<uint4*>(oh + j) = uh;
+                        if (ol) *reinterpret_cast<uint4*>(ol + j) = ul;
+                    }
+                }
+            }
+            if (p.out_f32) {
+                float* of = p.out_f32 + orow * p.out_f32_ld + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncnt) *reinterpret_cast<float4*>(of + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            }
+        }
+    }
+};
+
+
+// ---------------------------------------------------------------------------- transformer linear epilogues
+enum LinMode : int {
+    LIN_F32_ELU = 0,   // fp32 out; elu(x)+1 on output columns < elu_cols (q/k feature map of linear attention)
+    LIN_RELU_HL = 1,   // relu -> split-fp16 planes
+    LIN_LN = 2,        // LayerNorm over the full row (BN == d_model) [+ residual] -> fp32 and/or split-fp16 planes
+};
+
+struct LinEpiParams {
+    int M, N;
+    int mode;
+    int elu_cols;
+    const float* gamma;  // LIN_LN
+    const float* beta;
+    const float* resid;  // LIN_LN: optional fp32 residual x (out = x + LN(acc))
+    int resid_ld;
+    float* out_f32;
+    int out_f32_ld;
+    int out_col0;        // column offset added to n for the fp32 output
+    __half* out_hi;
+    __half* out_lo;
+    int out_ld;
+};
+
+struct LinEpi {
+    using Params = LinEpiParams;
+    template <int BN>
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+        const int row = row0 + lane;
+        const bool valid = row < p.M;
+        float mean = 0.f, rstd = 0.f;
+        if (p.mode == LIN_LN) {
+            // two passes over this thread's TMEM row (BN == N == d_model): mean, then variance
+            float s = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_warp + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s += v[j];
+            }
+            mean = s / static_cast<float>(BN);
+            float q = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_warp + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q += d * d; }
+            }
+            rstd = rsqrtf(q / static_cast<float>(BN) + 1e-5f);
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_warp + c0, v);
+            tmem_ld_wait();
+            const int nb = n0 + c0;
+            if (!valid || nb >= p.N) continue;
+            if (p.mode == LIN_F32_ELU) {
+                if (nb < p.elu_cols) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : expm1f(v[j]) + 1.f;
+                }
+            } else if (p.mode == LIN_RELU_HL) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + nb + j));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + nb + j));
+                    v[j] = (v[j] - mean) * rstd * g4.x + b4.x;
+                    v[j + 1] = (v[j + 1] - mean) * rstd * g4.y + b4.y;
+                    v[j + 2] = (v[j + 2] - mean) * rstd * g4.z + b4.z;
+                    v[j + 3] = (v[j + 3] - mean) * rstd * g4.w + b4.w;
+                }
+                if (p.resid) {
+                    const float* rr = p.resid + static_cast<long long>(row) * p.resid_ld + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
+                        v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+                    }
+                }
+            }
+            if (p.out_f32) {
+                float* of = p.out_f32 + static_cast<long long>(row) * p.out_f32_ld + p.out_col0 + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(of + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (p.out_hi) {
+                __half* oh = p.out_hi + static_cast<long long>(row) * p.out_ld + nb;
+                __half* ol = p.out_lo + static_cast<long long>(row) * p.out_ld + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 uh, ul;
+                    __half* hh = reinterpret_cast<__half*>(&uh);
+                    __half* hl = reinterpret_cast<__half*>(&ul);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) split_f16(v[j + q], hh[q], hl[q]);
+                    *reinterpret_cast<uint4*>(oh + j) = uh;
+                    *reinterpret_cast<uint4*>(ol + j) = ul;
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------- dual-softmax similarity epilogues
+// sim[i,j] = acc[i,j] * scale / temperature.   SIM_STATS: per-row (max, sum exp) over this CTA's BN columns, written
+// to part[blockIdx.y][row].  SIM_CONF: conf = softmax_row * softmax_col from finished row / column statistics; every
+// entry above thr competes for its row's and its column's best (64-bit atomicMax on (conf bits, ~index)).
+enum SimMode : int { SIM_STATS = 0, SIM_CONF = 1 };
+
+struct SimEpiParams {
+    int M, N;       // rows (tokens of A), columns (tokens of B)
+    int mode;
+    float scale;    // 1 / d_model
+    float temperature;
+    float2* part;   // SIM_STATS: [gridDim.y][M] (max, sumexp)
+    const float2* row_stat;  // SIM_CONF: [M] (max, sumexp)
+    const float2* col_stat;  // SIM_CONF: [N]
+    float thr;
+    unsigned long long* row_best;  // [M]
+    unsigned long long* col_best;  // [N]
+    float* conf_out;               // optional dense [M][N] (debug / small problems)
+};
+
+__device__ __forceinline__ unsigned long long pack_best(float conf, int idx) {
+    return (static_cast<unsigned long long>(__float_as_uint(conf)) << 32) | static_cast<unsigned int>(0x7fffffff - idx);
+}
+
+struct SimEpi {
+    using Params = SimEpiParams;
+    template <int BN>
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+        const int row = row0 + lane;
+        const bool valid = row < p.M;
+        if (p.mode == SIM_STATS) {
+            float m = -INFINITY, s = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_warp + c0, v);
+                tmem_ld_wait();
+                const int nb = n0 + c0;
+                float cm = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    v[j] = (nb + j < p.N) ? (v[j] * p.scale) / p.temperature : -INFINITY;
+                    cm = fmaxf(cm, v[j]);
+                }
+                if (cm > m) { s *= expf(m - cm); m = cm; }
+                if (m > -INFINITY) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s += expf(v[j] - m);
+                }
+            }
+            if (valid) p.part[static_cast<long long>(blockIdx.y) * p.M + row] = make_float2(m, s);
+        } else {
+            float2 rs = valid ? p.row_stat[row] : make_float2(0.f, 1.f);
+            float best = -1.f;
+            int best_j = 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld32(tmem_warp + c0, v);
+                tmem_ld_wait();
+                const int nb = n0 + c0;
+                if (!valid || nb >= p.N) continue;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (nb + j < p.N) {
+                        const float sim = (v[j] * p.scale) / p.temperature;
+                        const float2 cs = __ldg(p.col_stat + nb + j);
+                        const float conf = (expf(sim - rs.x) / rs.y) * (expf(sim - cs.x) / cs.y);
+                        if (p.conf_out) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
+                        if (conf > p.thr) {
+                            atomicMax(p.col_best + nb + j, pack_best(conf, row));
+                            if (conf > best) { best = conf; best_j = nb + j; }
+                        }
+                    }
+                }
+            }
+            if (valid && best >= 0.f) atomicMax(p.row_best + row, pack_best(best, best_j));
+        }
+    }
+};
+
+}  // namespace dfsfm

@@ -1,0 +1,133 @@
+// Host-side helpers: error handling, split-fp16 device buffers, TMA tensor-map encoding, engine launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gemm_engine.cuh"
+
+namespace dfsfm {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define DFSFM_CUDA(expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            throw ::dfsfm::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                                 std::to_string(__LINE__));                                                \
+    } while (0)
+
+#define DFSFM_CHECK(cond, msg)                                                   \
+    do {                                                                         \
+        if (!(cond)) throw ::dfsfm::Error(std::string("check failed: ") + (msg)); \
+    } while (0)
+
+// A split-fp16 activation / weight buffer: plane 0 = hi, plane 1 = lo, each [rows][C] row-major.
+struct HL {
+    __half* hi = nullptr;
+    long long rows = 0;
+    int C = 0;
+    __half* lo() const { return hi + rows * C; }
+    long long plane_elems() const { return rows * C; }
+    size_t bytes() const { return static_cast<size_t>(rows) * C * 2 * sizeof(__half); }
+};
+
+inline HL hl_alloc(long long rows, int C) {
+    HL b;
+    b.rows = rows;
+    b.C = C;
+    DFSFM_CUDA(cudaMalloc(&b.hi, b.bytes()));
+    DFSFM_CUDA(cudaMemset(b.hi, 0, b.bytes()));
+    return b;
+}
+inline void hl_free(HL& b) {
+    if (b.hi) cudaFree(b.hi);
+    b.hi = nullptr;
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DFSFM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        DFSFM_CHECK(q == cudaDriverEntryPointSuccess && p, "cuTensorMapEncodeTiled not available");
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// dims {C (inner), rows, 2 planes}; box {64, box_rows, 1}; 128-byte swizzle; OOB -> zeros.
+inline CUtensorMap make_tmap(const __half* base, int C, long long rows, long long plane_elems, int box_rows) {
+    CUtensorMap m;
+    memset(&m, 0, sizeof(m));
+    DFSFM_CHECK(C % 8 == 0, "tensor-map inner dim must be a multiple of 8 halves");
+    DFSFM_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor-map base must be 16-byte aligned");
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(rows), 2};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(C) * 2, static_cast<cuuint64_t>(plane_elems) * 2};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(base), dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed with code " + std::to_string(static_cast<int>(r)));
+    return m;
+}
+inline CUtensorMap make_tmap(const HL& b, int box_rows) { return make_tmap(b.hi, b.C, b.rows, b.plane_elems(), box_rows); }
+
+template <int BN, bool kSplit, class Epi>
+inline void launch_gemm(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, kSplit>;
+    auto kern = gemm_tc_kernel<BN, kSplit, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    dim3 grid((core.M + kBM - 1) / kBM, (n_total + BN - 1) / BN);
+    kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, core, ep);
+    DFSFM_CUDA(cudaGetLastError());
+}
+
+// Fill the tap table of a stride-1 k x k convolution on a flat-halo geometry with row pitch Wp.
+inline void conv_taps_s1(GemmCore& c, int k, int Wp) {
+    const int r = k / 2;
+    c.num_taps = k * k;
+    int t = 0;
+    for (int dy = -r; dy <= r; ++dy)
+        for (int dx = -r; dx <= r; ++dx, ++t) {
+            c.tap_map[t] = 0;
+            c.tap_shift[t] = dy * Wp + dx;
+        }
+}
+// 3x3 stride-2 convolution reading the four parity planes (map index = (dy&1)*2 + (dx&1)); Wp = OUTPUT pitch.
+inline void conv_taps_s2(GemmCore& c, int Wp) {
+    c.num_taps = 9;
+    int t = 0;
+    for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx, ++t) {
+            c.tap_map[t] = static_cast<int8_t>((dy & 1) * 2 + (dx & 1));
+            c.tap_shift[t] = (dy < 0 ? -Wp : 0) + (dx < 0 ? -1 : 0);
+        }
+}
+inline void set_k(GemmCore& c, int cpad) {
+    c.cpad = cpad;
+    c.kchunks = (cpad + 63) / 64;
+    const int rem = cpad - (c.kchunks - 1) * 64;
+    c.k16_last = (rem + 15) / 16;
+}
+
+}  // namespace dfsfm

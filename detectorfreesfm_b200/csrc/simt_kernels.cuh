@@ -1,0 +1,239 @@
+// Bandwidth-bound / small-contraction kernels (plain SIMT, fp32): stem conv, fp32->split-fp16 conversion,
+// linear-attention state reduction and application, dual-softmax statistics merge, mutual-NN selection.
+#pragma once
+#include "tc_common.cuh"
+
+namespace dfsfm {
+
+// --------------------------------------------------------------------------------------------------------
+// 7x7 stride-2 pad-3 convolution 1 -> 128 channels + folded BN + ReLU  (ResNetFPN_8_2.conv1/bn1/relu,
+// third_party/LoFTR/src/loftr/backbone/resnet_fpn.py:100-102).  Output: flat-halo split-fp16, pitch W/2+1.
+// CTA = 8x16 output pixels, thread = output channel.
+constexpr int kStemTH = 8, kStemTW = 16;
+static __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __restrict__ img, int H, int W, const float* __restrict__ w /*[128][49]*/,
+                                                        const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                                        __half* __restrict__ out_lo) {
+    constexpr int IH = kStemTH * 2 + 5, IW = kStemTW * 2 + 5;
+    __shared__ float tile[IH][IW + 1];
+    const int H2 = H / 2, W2 = W / 2, Wp = W2 + 1;
+    const int oy0 = blockIdx.y * kStemTH, ox0 = blockIdx.x * kStemTW;
+    const int n = blockIdx.z;
+    const float* im = img + static_cast<long long>(n) * H * W;
+    for (int i = threadIdx.x; i < IH * IW; i += 128) {
+        const int ty = i / IW, tx = i - ty * IW;
+        const int iy = oy0 * 2 - 3 + ty, ix = ox0 * 2 - 3 + tx;
+        tile[ty][tx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? im[static_cast<long long>(iy) * W + ix] : 0.f;
+    }
+    const int c = threadIdx.x;
+    float wr[49];
+#pragma unroll
+    for (int i = 0; i < 49; ++i) wr[i] = w[c * 49 + i];
+    const float b = bias[c];
+    __syncthreads();
+    const long long img_rows = static_cast<long long>(H2 + 1) * Wp;
+    for (int py = 0; py < kStemTH; ++py) {
+        const int oy = oy0 + py;
+        if (oy >= H2) break;
+        for (int px = 0; px < kStemTW; ++px) {
+            const int ox = ox0 + px;
+            if (ox >= W2) break;
+            float acc = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 7; ++kx) acc = fmaf(wr[ky * 7 + kx], tile[py * 2 + ky][px * 2 + kx], acc);
+            acc = fmaxf(acc + b, 0.f);
+            const long long o = (n * img_rows + static_cast<long long>(oy) * Wp + ox) * 128 + c;
+            __half h, l;
+            split_f16(acc, h, l);
+            out_hi[o] = h;
+            out_lo[o] = l;
+        }
+    }
+}
+
+// fp32 [rows][C] -> split-fp16 planes [rows][C]; C % 4 == 0.
+static __global__ void split_rows_kernel(const float* __restrict__ in, long long n4, __half* __restrict__ hi, __half* __restrict__ lo) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= n4) return;
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    __half h[4], l[4];
+    split_f16(v.x, h[0], l[0]);
+    split_f16(v.y, h[1], l[1]);
+    split_f16(v.z, h[2], l[2]);
+    split_f16(v.w, h[3], l[3]);
+    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
+    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+}
+
+// --------------------------------------------------------------------------------------------------------
+// Linear attention (third_party/LoFTR/src/loftr/loftr_module/linear_attention.py:20-47, identical maths in
+// src/MultiviewMatcher/matcher_module/linear_attention.py:28-60).  K has already been through elu+1 (GEMM epilogue).
+//   KV[h][d][v] = sum_s K[s,h,d] * (V[s,h,v] / len),  Ksum[h][d] = sum_s K[s,h,d]        (masked tokens skipped)
+//   out[l,h,v]  = (sum_d Q[l,h,d] KV[h][d][v]) * (1 / (sum_d Q[l,h,d] Ksum[h][d] + eps)) * len
+// A "segment" is one attention batch element (the whole image for HP-1, one track for HP-2).
+struct Seg {
+    int start;  // first token row
+    int count;  // tokens in the segment (incl. masked ones: `len` of the reference is the padded length)
+    int valid;  // leading tokens that are valid (kv_mask / q_mask); the rest are skipped
+    int state;  // index of the KV state this segment writes / reads
+};
+
+constexpr int kKvTokPerCta = 128;
+// grid (chunks, segments); block = 8 heads * D threads.  part: [seg][chunk][8*D*(D+1)]
+template <int D>
+static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* __restrict__ K, const float* __restrict__ V, int ld,
+                                                            const Seg* __restrict__ segs, int max_chunks, float* __restrict__ part) {
+    constexpr int C = 8 * D;
+    constexpr int SUB = 16;
+    __shared__ float Ks[SUB][C];
+    __shared__ float Vs[SUB][C];
+    const Seg sg = segs[blockIdx.y];
+    const int tid = threadIdx.x;
+    const int h = tid / D;
+    float acc[D];
+#pragma unroll
+    for (int v = 0; v < D; ++v) acc[v] = 0.f;
+    float ksum = 0.f;
+    const float len = static_cast<float>(sg.count);
+    const int t0 = blockIdx.x * kKvTokPerCta;
+    const int t1 = min(t0 + kKvTokPerCta, sg.valid);
+    for (int tb = t0; tb < t1; tb += SUB) {
+        const int nt = min(SUB, t1 - tb);
+        __syncthreads();
+        for (int i = tid; i < nt * C; i += C) {
+            const int s = i / C, c = i - s * C;
+            const long long r = static_cast<long long>(sg.start + tb + s) * ld + c;
+            Ks[s][c] = K[r];
+            Vs[s][c] = V[r] / len;
+        }
+        __syncthreads();
+        for (int s = 0; s < nt; ++s) {
+            const float k = Ks[s][tid];
+            ksum += k;
+#pragma unroll
+            for (int v = 0; v < D; ++v) acc[v] = fmaf(k, Vs[s][h * D + v], acc[v]);
+        }
+    }
+    float* o = part + (static_cast<long long>(blockIdx.y) * max_chunks + blockIdx.x) * (C * (D + 1)) + tid * (D + 1);
+#pragma unroll
+    for (int v = 0; v < D; ++v) o[v] = acc[v];
+    o[D] = ksum;
+}
+// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic)
+template <int D>
+static __global__ void kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs, int max_chunks, float* __restrict__ state) {
+    constexpr int SZ = 8 * D * (D + 1);
+    const Seg sg = segs[blockIdx.x];
+    const int nch = (sg.valid + kKvTokPerCta - 1) / kKvTokPerCta;
+    for (int i = threadIdx.x; i < SZ; i += blockDim.x) {
+        float s = 0.f;
+        for (int c = 0; c < nch; ++c) s += part[(static_cast<long long>(blockIdx.x) * max_chunks + c) * SZ + i];
+        state[static_cast<long long>(sg.state) * SZ + i] = s;
+    }
+}
+// grid (token blocks of 64, segments); block 256 = 8 warps; each warp handles 8 tokens.  lane -> (head-in-group, v).
+// Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
+template <int D>
+static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, int ldq, const Seg* __restrict__ segs,
+                                                          const float* __restrict__ state, __half* __restrict__ out_hi,
+                                                          __half* __restrict__ out_lo, int ldo) {
+    constexpr int C = 8 * D;
+    constexpr int SZ = C * (D + 1);
+    constexpr int HPW = 32 / D;  // heads handled per warp pass
+    __shared__ float st[SZ];
+    const Seg sg = segs[blockIdx.y];
+    if (blockIdx.x * 64 >= sg.count) return;
+    for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int hs = lane / D, v = lane - hs * D;
+    const float len = static_cast<float>(sg.count);
+    for (int ti = 0; ti < 8; ++ti) {
+        const int t = blockIdx.x * 64 + warp * 8 + ti;
+        if (t >= sg.count) break;
+        const long long row = sg.start + t;
+        const bool tok_valid = t < sg.valid;
+        for (int hg = 0; hg < 8; hg += HPW) {
+            const int h = hg + hs;
+            const float q = tok_valid ? Q[row * ldq + h * D + v] : 0.f;  // here lane's "v" plays the role of d
+            float z = q * st[(h * D + v) * (D + 1) + D];
+#pragma unroll
+            for (int o = D / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float qd = __shfl_sync(0xffffffffu, q, hs * D + d);
+                acc = fmaf(qd, st[(h * D + d) * (D + 1) + v], acc);
+            }
+            const float r = acc * (1.f / (z + 1e-6f)) * len;
+            __half hh, ll;
+            split_f16(r, hh, ll);
+            out_hi[row * ldo + h * D + v] = hh;
+            out_lo[row * ldo + h * D + v] = ll;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------------------
+// merge per-column-tile softmax partials: stat[i] = (max, sum exp(. - max))
+static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T, int M, float2* __restrict__ stat) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) m = fmaxf(m, part[static_cast<long long>(t) * M + i].x);
+    float s = 0.f;
+    for (int t = 0; t < T; ++t) {
+        const float2 p = part[static_cast<long long>(t) * M + i];
+        s += p.y * expf(p.x - m);
+    }
+    stat[i] = make_float2(m, s);
+}
+
+// Mutual-nearest-neighbour selection + ordered compaction (CoarseMatching.get_coarse_match,
+// third_party/LoFTR/src/loftr/utils/coarse_matching.py:172-193).  One CTA of 1024 threads walks the rows in order.
+// mask_border quirk: only the LEADING `border` rows/cols of each grid axis are removed (:8-22).
+static __global__ void __launch_bounds__(1024) match_select_kernel(const unsigned long long* __restrict__ row_best,
+                                                            const unsigned long long* __restrict__ col_best, int L, int w0c, int w1c,
+                                                            int border, int capacity, int* __restrict__ i_ids, int* __restrict__ j_ids,
+                                                            float* __restrict__ mconf, int* __restrict__ count) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < L; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        int flag = 0, j = 0;
+        float conf = 0.f;
+        if (i < L) {
+            const unsigned long long rb = row_best[i];
+            if (rb != 0ull) {
+                conf = __uint_as_float(static_cast<unsigned int>(rb >> 32));
+                j = 0x7fffffff - static_cast<int>(rb & 0xffffffffu);
+                const unsigned long long cb = col_best[j];
+                const bool mutual = static_cast<unsigned int>(cb >> 32) == static_cast<unsigned int>(rb >> 32);
+                const bool inb = (i / w0c >= border) && (i % w0c >= border) && (j / w1c >= border) && (j % w1c >= border);
+                flag = (mutual && inb && conf != 0.f) ? 1 : 0;
+            }
+        }
+        const unsigned int bal = __ballot_sync(0xffffffffu, flag);
+        const int wpre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_sums[w];
+        const int pos = base + woff + wpre;
+        if (flag && pos < capacity) {
+            i_ids[pos] = i;
+            j_ids[pos] = j;
+            mconf[pos] = conf;
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) base = pos + flag;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
+}
+
+}  // namespace dfsfm

@@ -1,0 +1,91 @@
+/* dfsfm_b200 -- C ABI of the B200-native dense-matching engine for DetectorFreeSfM's two hot paths.
+ *
+ * Plain pointers and sizes only; every pointer named *_dev is a CUDA device pointer on the engine's device, every
+ * `stream` is a cudaStream_t passed as void*.  All functions return 0 on success and a non-zero code on failure;
+ * dfsfm_last_error() then returns a description (thread-local).  No exception crosses this boundary, nothing here
+ * falls back to the CPU.
+ *
+ * Reference interfaces replaced (paths relative to zju3dv/DetectorFreeSfM):
+ *   HP-1  third_party/LoFTR/src/loftr/loftr.py:29-81  LoFTR.forward, called from
+ *         src/coarse_match/coarse_match_worker.py:94-100 (extract_matches) behind the NEUSFM_coarse_matcher hook.
+ *   HP-2  src/MultiviewMatcher/MultiviewMatcher.py:59-405  MultiviewMatcher.forward, called from
+ *         src/post_optimization/matcher_model/multiview_match_worker.py:59-64 (extract_results) per refinement chunk.
+ *   L0    third_party/RoIAlign.pytorch/roi_align/src/crop_and_resize_gpu.cpp:18-61 crop_and_resize_gpu_forward.
+ */
+#ifndef DFSFM_B200_H_
+#define DFSFM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dfsfm_last_error(void);
+int dfsfm_version(void);
+
+/* ------------------------------------------------------------------------------------------------ HP-1: coarse matcher */
+typedef struct dfsfm_coarse dfsfm_coarse_t;
+
+/* LoFTR(config) construction (loftr.py:12-27).  d_model=256, nhead=8, 8 layers ['self','cross']*4 (default.py:14-24). */
+int dfsfm_coarse_create(dfsfm_coarse_t** out, int device);
+void dfsfm_coarse_destroy(dfsfm_coarse_t* h);
+
+/* Upload one packed parameter (host fp32, row-major [rows][cols]).  kind 0: matrix stored as split-fp16 GEMM operand,
+ * kind 1: fp32 vector/table.  Names and packing: detectorfreesfm_b200/packing.py (state_dict -> BN-folded operands). */
+int dfsfm_coarse_set_param(dfsfm_coarse_t* h, const char* name, const float* host, int64_t rows, int64_t cols, int kind);
+
+/* ResNetFPN_8_2 (coarse sub-graph) + PositionEncodingSine + 'n c h w -> n (h w) c'  (loftr.py:45-59):
+ * image_dev [H][W] fp32 in [0,1] (H, W multiples of 8), pe_dev [(H/8)*(W/8)][256] fp32,
+ * tokens_out_dev [(H/8)*(W/8)][256] fp32.  Exact per image, hence cacheable across pairs. */
+int dfsfm_coarse_features(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev,
+                          void* stream);
+
+/* LocalFeatureTransformer.forward (loftr_module/transformer.py:80-101), in place on feat0_dev [L][256], feat1_dev [S][256]. */
+int dfsfm_coarse_transformer(dfsfm_coarse_t* h, float* feat0_dev, int L, float* feat1_dev, int S, void* stream);
+
+/* CoarseMatching.forward + get_coarse_match (utils/coarse_matching.py:84-258, dual-softmax, inference, no padding masks):
+ * writes up to `capacity` matches in ascending i order: i_ids/j_ids int32, mconf fp32, and their number to n_matches_dev.
+ * conf_out_dev: optional dense [L][S] confidence matrix (NULL in production). */
+int dfsfm_coarse_match(dfsfm_coarse_t* h, const float* feat0_dev, int h0c, int w0c, const float* feat1_dev, int h1c, int w1c, float thr,
+                       int border_rm, float temperature, int32_t* i_ids_dev, int32_t* j_ids_dev, float* mconf_dev,
+                       int32_t* n_matches_dev, int capacity, float* conf_out_dev, void* stream);
+
+/* ---------------------------------------------------------------------------------- L0: RoIAlign (crop_and_resize) */
+/* crop_and_resize_gpu_forward (crop_and_resize_gpu.cpp:18-61): image NCHW fp32, boxes [n][4] = (y1,x1,y2,x2) normalised,
+ * box_index [n] int32, crops [n][C][crop_h][crop_w] fp32. */
+int dfsfm_crop_and_resize_forward(const float* image_dev, int batch, int depth, int image_h, int image_w, const float* boxes_dev,
+                                  const int32_t* box_index_dev, int num_boxes, float extrapolation_value, int crop_h, int crop_w,
+                                  float* crops_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------ HP-2: refinement matcher */
+typedef struct dfsfm_refine dfsfm_refine_t;
+
+/* MultiviewMatcher(config, test=True) (MultiviewMatcher.py:17-57) with window W, left window LW
+ * (multiview_match_worker.py:20-34 rescales them per refinement iteration). */
+int dfsfm_refine_create(dfsfm_refine_t** out, int device, int window, int left_window);
+void dfsfm_refine_destroy(dfsfm_refine_t* h);
+int dfsfm_refine_set_param(dfsfm_refine_t* h, const char* name, const float* host, int64_t rows, int64_t cols, int kind);
+
+/* MultiviewMatcher.forward on one chunk (MultiviewMatcher.py:59-405, n_steps=1, chunk_backbone_img path).
+ * images_dev[i]: [3][H_i][W_i] fp32 RGB;  scales_hw [n_img][2] host (h, w ratios);  M tracks, Nq = n_view-1 query slots.
+ * query_pts [M][2], ref_pts [Nq][M][2], valid [Nq][M] (uint8), q_img_idx [M], r_img_idx [Nq][M] (-1 = pad), movable [M]:
+ * all HOST arrays (the per-chunk dict of construct_matching_data.py:317-476).
+ * Outputs (HOST): query_refined [M][2], ref_refined [Nq][M][2], std_out [Nq][M]. */
+int dfsfm_refine_chunk(dfsfm_refine_t* h, int n_img, const float* const* images_dev, const int32_t* H, const int32_t* W,
+                       const float* scales_hw, int M, int Nq, const float* query_pts, const float* ref_pts, const uint8_t* valid,
+                       const int32_t* q_img_idx, const int32_t* r_img_idx, const uint8_t* movable, float* query_refined,
+                       float* ref_refined, float* std_out, void* stream);
+
+/* -------------------------------------------------------------------------------------------------- test / bench hooks */
+/* Shifted-row GEMM engine on raw split-fp16 operands: out[M][N] fp32 = sum_t A[p+shift_t, :cpad] . W[n, t*cpad : (t+1)*cpad].
+ * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */
+int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts,
+                     int cpad, int bn, int split, float* out_dev, int M, int N, void* stream);
+/* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
+int64_t dfsfm_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFSFM_B200_H_ */

@@ -1,0 +1,225 @@
+"""Import the UNMODIFIED reference modules from /root/reference on CPU.
+
+TEST INFRASTRUCTURE, build-container only (the GPU box has no /root/reference): used by
+tests/test_oracle_vs_reference.py and tests/golden/make_golden.py to pin the oracle
+restatement against the reference itself.  Nothing is copied; the reference's files are
+imported where they lie, behind stubs for its un-installed third-party deps
+(kornia 0.4.1: two functions; yacs CfgNode; omegaconf; timm registry; loguru) --
+SURVEY.md section 8(c).
+"""
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+REF = os.environ.get("DFSFM_REFERENCE", "/root/reference")
+
+
+def available():
+    return os.path.isdir(os.path.join(REF, "third_party", "LoFTR"))
+
+
+def _mod(name, **attrs):
+    m = sys.modules.get(name)
+    if m is None:
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    for k, v in attrs.items():
+        setattr(m, k, v)
+    return m
+
+
+def _install_stubs():
+    from . import loftr_oracle as lo
+    import torch
+
+    def spatial_expectation2d(inp, normalized_coordinates=True):
+        return lo.spatial_expectation2d(inp)
+
+    def create_meshgrid(h, w, normalized_coordinates=True, device=None):
+        return lo.create_meshgrid(h, w).to(device) if device is not None else lo.create_meshgrid(h, w)
+
+    try:
+        import kornia  # noqa: F401
+    except Exception:
+        _mod("kornia")
+        _mod("kornia.geometry")
+        _mod("kornia.geometry.subpix")
+        dsnt = _mod("kornia.geometry.subpix.dsnt", spatial_expectation2d=spatial_expectation2d)
+        sys.modules["kornia.geometry.subpix"].dsnt = dsnt
+        _mod("kornia.utils")
+        _mod("kornia.utils.grid", create_meshgrid=create_meshgrid)
+    try:
+        import yacs  # noqa: F401
+    except Exception:
+        class CfgNode(dict):
+            def __getattr__(self, k):
+                try:
+                    return self[k]
+                except KeyError:
+                    raise AttributeError(k)
+
+            def __setattr__(self, k, v):
+                self[k] = v
+        _mod("yacs")
+        _mod("yacs.config", CfgNode=CfgNode)
+    try:
+        import omegaconf  # noqa: F401
+    except Exception:
+        class _Conf(dict):
+            def __getattr__(self, k):
+                try:
+                    return self[k]
+                except KeyError:
+                    raise AttributeError(k)
+
+        class OmegaConf:
+            @staticmethod
+            def merge(*cfgs):
+                out = _Conf()
+                for c in cfgs:
+                    out.update(dict(c))
+                return out
+
+            @staticmethod
+            def set_struct(c, v):
+                pass
+
+            @staticmethod
+            def set_readonly(c, v):
+                pass
+        _mod("omegaconf", OmegaConf=OmegaConf)
+    try:
+        import timm  # noqa: F401
+    except Exception:
+        _mod("timm")
+        _mod("timm.models")
+        _mod("timm.models.registry", register_model=lambda f: f)
+        _mod("timm.models.layers", DropPath=torch.nn.Identity, trunc_normal_=lambda *a, **k: None,
+             to_2tuple=lambda x: (x, x))
+    try:
+        import loguru  # noqa: F401
+    except Exception:
+        import logging
+        _mod("loguru", logger=logging.getLogger("ref"))
+
+
+def import_loftr():
+    """-> (LoFTR class, default_cfg dict) from third_party/LoFTR/src/loftr."""
+    _install_stubs()
+    root = os.path.join(REF, "third_party", "LoFTR")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    # 'src' here is third_party/LoFTR/src; keep it out of the way of the main repo's src
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    mod = importlib.import_module("src.loftr")
+    LoFTR, default_cfg = mod.LoFTR, mod.default_cfg
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        sys.modules["_loftr_" + k] = sys.modules.pop(k)
+    sys.path.remove(root)
+    return LoFTR, default_cfg
+
+
+def loftr_config(thr=0.2, fine=False, temperature=0.1):
+    """The dict coarse_match_worker.build_model produces (coarse_match_worker.py:31-36)."""
+    import copy
+    _, default_cfg = import_loftr()
+    cfg = copy.deepcopy(default_cfg)
+    cfg["coarse"]["temp_bug_fix"] = False
+    cfg["match_coarse"]["thr"] = thr
+    cfg["match_coarse"]["dsmax_temperature"] = temperature
+    cfg["match_coarse"]["skh_prefilter"] = False
+    cfg["match_coarse"]["sparse_spvs"] = True
+    cfg["fine"]["enable"] = fine
+    return cfg
+
+
+_ROI_EXT = None
+
+
+def build_ref_roialign():
+    """Compile the reference's own CPU RoIAlign (crop_and_resize.cpp, OpenMP) from the
+    sources where they lie into oracle/_ref/ (git-ignored; travels to the GPU box)."""
+    global _ROI_EXT
+    if _ROI_EXT is not None:
+        return _ROI_EXT
+    from torch.utils.cpp_extension import load
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    os.makedirs(out, exist_ok=True)
+    src = os.path.join(REF, "third_party", "RoIAlign.pytorch", "roi_align", "src", "crop_and_resize.cpp")
+    # the image has no libgomp.spec, so -fopenmp is unavailable: the OpenMP pragma (crop_and_resize.cpp:31) is
+    # ignored and the reference op runs single-threaded -- same arithmetic.
+    _ROI_EXT = load(name="crop_and_resize_cpu", sources=[src], build_directory=out,
+                    extra_cflags=["-O2", "-w"], verbose=False)
+    return _ROI_EXT
+
+
+def load_prebuilt_ref_roialign():
+    """Load oracle/_ref/crop_and_resize_cpu.so if it was built (works without /root/reference)."""
+    global _ROI_EXT
+    if _ROI_EXT is not None:
+        return _ROI_EXT
+    import torch  # noqa: F401  (the .so links against libtorch)
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "crop_and_resize_cpu.so")
+    if not os.path.exists(so):
+        return None
+    spec = importlib.util.spec_from_file_location("crop_and_resize_cpu", so)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    _ROI_EXT = m
+    return m
+
+
+def import_multiview():
+    """-> MultiviewMatcher class from src/MultiviewMatcher (never executes src/__init__.py)."""
+    _install_stubs()
+    ext = build_ref_roialign()
+    roi_dir = os.path.join(REF, "third_party", "RoIAlign.pytorch", "roi_align")
+    pkg = _mod("roi_align")
+    pkg.__path__ = [roi_dir]
+    sys.modules["roi_align.crop_and_resize_cpu"] = ext
+    pkg.crop_and_resize_cpu = ext
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    utils = _mod("src.utils")
+    utils.__path__ = []  # block the real src/utils (needs ray, h5py, ...)
+
+    class PassThroughProfiler:
+        def record_function(self, name):
+            import contextlib
+            return contextlib.nullcontext()
+    _mod("src.utils.profiler", PassThroughProfiler=PassThroughProfiler)
+    mod = importlib.import_module("src.MultiviewMatcher.MultiviewMatcher")
+    return mod.MultiviewMatcher
+
+
+def multiview_config(window=15, left_window=7):
+    """model.multiview_refinement of hydra_training_configs/experiment/
+    multiview_refinement_matching.yaml:22-90, with the per-iteration window rescale of
+    multiview_match_worker.py:20-34 already applied and pretrained=None (no network)."""
+    mm = {"enable": True, "type": "s2d", "detector": "OnGrid", "window_size": window,
+          "best_left_strategy": "smallest_mean_std",
+          "s2d": {"type": "heatmap", "obtain_offset_method": "argsoftmax"}}
+    return {
+        "n_matching_steps": 1, "enable_multiview_scale_align": False,
+        "backbone": {"type": "S2DNet", "resolution": [4, 1],
+                     "s2dnet": {"name": "s2dnet", "num_layers": 2, "window_size": window,
+                                "checkpointing": None, "output_dim": 128, "pretrained": None,
+                                "substitute_pooling_layers": True, "combine": True,
+                                "zoomin_strategy": "post"},
+                     "pretrained": None, "pretrained_fix": False},
+        "use_fine_backbone_as_coarse": False, "interpol_type": "bilinear",
+        "multiview_transform": {"sparse": True, "crop_size": 35, "window_size": window,
+                                "enable_rescaled_crop": False, "enable": True, "type": "LoFTR",
+                                "d_model": 128, "nhead": 8, "layer_names": ["self", "cross"],
+                                "layer_iter_n": 2, "dropout": 0.0, "attention": "linear",
+                                "norm_method": "layernorm", "attention_type": "multiview",
+                                "kernel_fn": "elu + 1", "d_kernel": 16, "redraw_interval": 2,
+                                "rezero": None, "final_proj": False},
+        "multiview_matching_train": {**mm, "left_point_movement_window_size": None},
+        "multiview_matching_test": {**mm, "left_point_movement_window_size": left_window},
+    }

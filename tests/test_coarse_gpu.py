@@ -1,0 +1,87 @@
+"""HP-1 parity on the GPU: B200LoFTR (C ABI, sm_100a kernels) vs the CPU oracle (oracle/loftr_oracle.py) on identical
+seeded weights and inputs.  Tolerances: north_star -- match confidences within 1e-3; index sets identical."""
+import pytest
+import torch
+
+from oracle import loftr_oracle as lo
+from oracle import weights
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return weights.loftr_state_dict(0)
+
+
+@pytest.fixture(scope="module")
+def matcher(sd):
+    from detectorfreesfm_b200 import B200LoFTR
+    m = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1)).cuda().eval()
+    m.load_state_dict(sd)
+    return m
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp(min=1e-12)).item()
+
+
+@pytest.mark.parametrize("hw", [(96, 128), (64, 64), (120, 88)])
+def test_backbone_features(matcher, sd, hw):
+    im = util.synth_image(hw[0], hw[1], seed=3)
+    x3, _ = lo.resnet_fpn_8_2(im, sd, fine=False)
+    h, w = x3.shape[2:]
+    ref = (x3 + lo.position_encoding_sine(256, h, w)[None]).flatten(2).transpose(1, 2)[0]
+    out = matcher.extract_features(im.cuda()).cpu()
+    assert out.shape == ref.shape
+    assert rel_err(out, ref) < 2e-5, rel_err(out, ref)
+
+
+def test_transformer(matcher, sd):
+    g = torch.Generator().manual_seed(5)
+    f0 = torch.randn(1, 300, 256, generator=g)
+    f1 = torch.randn(1, 417, 256, generator=g)
+    r0, r1 = lo.local_feature_transformer(f0, f1, sd, "loftr_coarse", ["self", "cross"] * 4, 8)
+    o0, o1 = matcher.transform(f0[0].cuda().clone(), f1[0].cuda().clone())
+    assert rel_err(o0.cpu(), r0[0]) < 5e-5, rel_err(o0.cpu(), r0[0])
+    assert rel_err(o1.cpu(), r1[0]) < 5e-5, rel_err(o1.cpu(), r1[0])
+
+
+@pytest.mark.parametrize("hw0,hw1,thr", [((20, 24), (20, 24), 0.2), ((24, 30), (18, 26), 0.2), ((16, 16), (16, 16), 0.0),
+                                         ((40, 52), (44, 48), 0.2)])
+def test_coarse_matching_stage(matcher, hw0, hw1, thr):
+    """dual-softmax + mutual-NN on synthetic discriminative features (thousands of candidate matches)."""
+    L, S = hw0[0] * hw0[1], hw1[0] * hw1[1]
+    f0, f1 = util.discriminative_features(L, S, seed=L + S)
+    conf = lo.dual_softmax_conf(f0[None], f1[None], 0.1)
+    ref = lo.get_coarse_match(conf, hw0, hw1, (hw0[0] * 8, hw0[1] * 8), thr, 2)
+    matcher.thr = thr
+    try:
+        i_ids, j_ids, mconf, cm = matcher.coarse_match(f0.cuda(), hw0, f1.cuda(), hw1, return_conf=True)
+    finally:
+        matcher.thr = 0.2
+    assert (cm.cpu() - conf[0]).abs().max().item() < 1e-3
+    assert len(ref["i_ids"]) > 10
+    assert torch.equal(i_ids.cpu(), ref["i_ids"]) and torch.equal(j_ids.cpu(), ref["j_ids"])
+    assert (mconf.cpu() - ref["mconf"]).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("temperature,thr", [(0.1, 0.2), (0.01, 0.2), (0.01, 0.0)])
+def test_end_to_end_pair(sd, temperature, thr):
+    from detectorfreesfm_b200 import B200LoFTR
+    m = B200LoFTR(util.loftr_config(thr=thr, temperature=temperature)).cuda().eval()
+    m.load_state_dict(sd)
+    im0, im1 = util.synth_pair(96, 128, seed=1)
+    scale0, scale1 = torch.tensor([[1.5, 1.25]]), torch.tensor([[1.0, 2.0]])
+    ref = lo.loftr_forward({"image0": im0, "image1": im1, "scale0": scale0, "scale1": scale1}, sd,
+                           {"thr": thr, "temperature": temperature}, keep=True)
+    data = {"image0": im0.cuda(), "image1": im1.cuda(), "scale0": scale0.cuda(), "scale1": scale1.cuda(),
+            "_return_conf_matrix": True}
+    m(data)
+    assert (data["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() < 1e-3
+    assert torch.equal(data["i_ids"].cpu(), ref["i_ids"]) and torch.equal(data["j_ids"].cpu(), ref["j_ids"])
+    if len(ref["mconf"]):
+        assert (data["mconf"].cpu() - ref["mconf"]).abs().max().item() < 1e-3
+        assert torch.equal(data["mkpts0_f"].cpu(), ref["mkpts0_f"]) and torch.equal(data["mkpts1_f"].cpu(), ref["mkpts1_f"])
+    assert (data["m_bids"] == 0).all()
