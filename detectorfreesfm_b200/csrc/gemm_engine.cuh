@@ -50,7 +50,13 @@ struct GemmCfg {
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-    static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    // Two accumulators in TMEM: the main one takes hi*hi, the correction one (kCorrOff columns further) takes
+    // hi*lo + lo*hi.  Tensor-core fp32 accumulation truncates, so keeping the 2^-11-sized terms out of the large
+    // accumulator cuts both the number of truncating adds into it (3x) and the rounding bias; they are summed
+    // in the epilogue with round-to-nearest.
+    static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int kCorrOff = kSplit ? kAccCols : 0;
+    static constexpr int kTmemCols = kSplit ? 2 * kAccCols : kAccCols;
     static_assert(kStages >= 2, "tile too large");
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "invalid UMMA N");
 };
@@ -118,6 +124,7 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
             int s = 0;
             uint32_t phase = 0;
             uint32_t acc = 0;
+            const uint32_t tmem_corr = tmem_base + Cfg::kCorrOff;
             for (int it = 0; it < n_iters; ++it) {
                 const int c = it % core.kchunks;
                 mbar_wait(&full_bar[s], phase);
@@ -129,13 +136,13 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
                     const uint64_t da = make_smem_desc_sw128(a_hi + k * 32);
                     const uint64_t db = make_smem_desc_sw128(b_hi + k * 32);
                     umma_f16(tmem_base, da, db, idesc, acc);
-                    acc = 1;
                     if (kSplit) {
                         const uint64_t dal = make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32);
                         const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + k * 32);
-                        umma_f16(tmem_base, da, dbl, idesc, 1);
-                        umma_f16(tmem_base, dal, db, idesc, 1);
+                        umma_f16(tmem_corr, da, dbl, idesc, acc);
+                        umma_f16(tmem_corr, dal, db, idesc, 1);
                     }
+                    acc = 1;
                 }
                 umma_commit(&empty_bar[s]);
                 if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
@@ -147,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        Epi::template run<BN>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0);
+        Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0);
         tc_fence_before();
     }
     __syncthreads();
@@ -158,6 +165,21 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
+// 32 accumulator columns of this thread's row: main (+ correction accumulator, added with round-to-nearest).
+template <int kCorr>
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float* v) {
+    tmem_ld32(taddr, v);
+    if (kCorr > 0) {
+        float w[32];
+        tmem_ld32(taddr + kCorr, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += w[j];
+    } else {
+        tmem_ld_wait();
+    }
+}
+
 // Geometry of a "flat halo" index space: image n, row y, col x  <->  p = n*Hp*Wp + y*Wp + x with Hp = H+1, Wp = W+1.
 // Column x == W and row y == H are zero halo cells shared by neighbouring rows / images: they are zeroed when the
 // buffer is allocated and never written afterwards, so a conv tap (dy,dx) is the row shift dy*Wp + dx.
@@ -193,7 +215,7 @@ struct ConvEpiParams {
 
 struct ConvEpi {
     using Params = ConvEpiParams;
-    template <int BN>
+    template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;
         bool valid = row < p.M;
@@ -221,8 +243,7 @@ struct ConvEpi {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem_warp + c0, v);  // warp-collective: every lane executes it
-            tmem_ld_wait();
+            load_acc32<kCorr>(tmem_warp + c0, v);  // warp-collective: every lane executes it
             const int nb = n0 + c0;
             if (!valid || nb >= p.N) continue;
             const int ncnt = p.N - nb;  // columns to write in this chunk (a multiple of 8; may exceed 32)
@@ -322,7 +343,7 @@ struct LinEpiParams {
 
 struct LinEpi {
     using Params = LinEpiParams;
-    template <int BN>
+    template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
@@ -333,8 +354,7 @@ struct LinEpi {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem_warp + c0, v);
-                tmem_ld_wait();
+                load_acc32<kCorr>(tmem_warp + c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s += v[j];
             }
@@ -343,8 +363,7 @@ struct LinEpi {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem_warp + c0, v);
-                tmem_ld_wait();
+                load_acc32<kCorr>(tmem_warp + c0, v);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q += d * d; }
             }
@@ -353,8 +372,7 @@ struct LinEpi {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             float v[32];
-            tmem_ld32(tmem_warp + c0, v);
-            tmem_ld_wait();
+            load_acc32<kCorr>(tmem_warp + c0, v);
             const int nb = n0 + c0;
             if (!valid || nb >= p.N) continue;
             if (p.mode == LIN_F32_ELU) {
@@ -433,7 +451,7 @@ __device__ __forceinline__ unsigned long long pack_best(float conf, int idx) {
 
 struct SimEpi {
     using Params = SimEpiParams;
-    template <int BN>
+    template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
@@ -442,8 +460,7 @@ struct SimEpi {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem_warp + c0, v);
-                tmem_ld_wait();
+                load_acc32<kCorr>(tmem_warp + c0, v);
                 const int nb = n0 + c0;
                 float cm = -INFINITY;
 #pragma unroll
@@ -465,8 +482,7 @@ struct SimEpi {
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
-                tmem_ld32(tmem_warp + c0, v);
-                tmem_ld_wait();
+                load_acc32<kCorr>(tmem_warp + c0, v);
                 const int nb = n0 + c0;
                 if (!valid || nb >= p.N) continue;
 #pragma unroll

@@ -42,3 +42,48 @@ def loftr_config(thr=0.2, temperature=0.1, fine=False):
                          "train_pad_num_gt_min": 200, "sparse_spvs": True},
         "fine": {"enable": fine, "d_model": 128, "d_ffn": 128, "nhead": 8, "layer_names": ["self", "cross"], "attention": "linear"},
     }
+
+
+def synth_chunk(M=64, n_img=6, max_views=5, hw=(120, 160), seed=0, scales=None, frozen_frac=0.2):
+    """One refinement chunk dict like MatchingMultiviewData.__getitem__ (construct_matching_data.py:317-476) after the
+    DataLoader added the batch dim: tracks sorted by #valid query views (descending, :350-352), valid views first,
+    -1 image index in the padded slots.  max_views = n_view - 1 (query slots)."""
+    g = torch.Generator().manual_seed(seed)
+    Nq = max_views
+    H, W = hw
+    images = [synth_image(H + 8 * (i % 3), W + 8 * ((i + 1) % 2), seed * 100 + i, channels=3) for i in range(n_img)]
+    if scales is None:
+        scales = torch.stack([torch.tensor([1.0 + 0.25 * (i % 3), 1.0 + 0.5 * (i % 2)]) for i in range(n_img)])[None]
+    counts = torch.randint(1, Nq + 1, (M,), generator=g).sort(descending=True)[0]
+    counts[0] = Nq
+    q_img = torch.randint(0, n_img, (M,), generator=g)
+    r_img = torch.full((Nq, M), -1, dtype=torch.long)
+    valid = torch.zeros(Nq, M, dtype=torch.bool)
+    for t in range(M):
+        others = [i for i in torch.randperm(n_img, generator=g).tolist() if i != int(q_img[t])]
+        k = min(int(counts[t]), len(others))
+        counts[t] = k
+        for v in range(k):
+            r_img[v, t] = others[v]
+            valid[v, t] = True
+    order = counts.sort(descending=True, stable=True)[1]
+    counts, q_img, r_img, valid = counts[order], q_img[order], r_img[:, order], valid[:, order]
+
+    def pts(img_idx):
+        """random points in ORIGINAL-image px, some close to the border so that crops leave the image"""
+        idx = img_idx.clamp(min=0)
+        hh = torch.tensor([im.shape[2] for im in images], dtype=torch.float32)[idx]
+        ww = torch.tensor([im.shape[3] for im in images], dtype=torch.float32)[idx]
+        u = torch.rand(*img_idx.shape, 2, generator=g)
+        x = (4 + u[..., 0] * (ww - 8)) * scales[0][idx][..., 1]
+        y = (4 + u[..., 1] * (hh - 8)) * scales[0][idx][..., 0]
+        return torch.stack([x, y], -1)
+
+    movable = torch.rand(M, generator=g) >= frozen_frac
+    return {
+        "images": images, "scales": scales.float(),
+        "query_points": pts(q_img)[None], "reference_points_coarse": pts(r_img)[None],
+        "track_valid_mask": valid[None], "query_img_idxs": q_img[None], "reference_img_idxs": r_img[None],
+        "query_movable_mask": movable[None],
+        "scales_relative": torch.ones(1, Nq + 1, M), "view_point_vector": torch.zeros(1, Nq + 1, M, 3),
+    }
