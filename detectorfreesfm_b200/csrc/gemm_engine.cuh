@@ -191,7 +191,8 @@ enum OutMode : int {
     OUT_FLAT = 0,    // same flat geometry as the input index space
     OUT_PARITY = 1,  // four half-resolution parity planes (feeds a stride-2 conv)
     OUT_DENSE = 2,   // dense token rows n*H*W + y*W + x
-    OUT_WINDOW = 3,  // a (wh x ww) window at (y0,x0) re-packed into its own flat-halo geometry
+    OUT_WINDOW = 3,  // a (wh x ww) window at (y0,x0) re-packed into its own flat-halo geometry (ohp x owp per image)
+    OUT_WINDOW_DENSE = 4,  // the window re-packed into dense rows n*wh*ww + y*ww + x
 };
 
 struct ConvEpiParams {
@@ -210,7 +211,8 @@ struct ConvEpiParams {
     long long plane_stride;  // OUT_PARITY: elements between consecutive parity planes
     float* out_f32;          // optional fp32 copy (same row mapping as out_hi)
     int out_f32_ld;
-    int wy0, wx0, wh, ww;    // OUT_WINDOW
+    int wy0, wx0, wh, ww;    // OUT_WINDOW / OUT_WINDOW_DENSE
+    int ohp, owp;            // OUT_WINDOW: rows / pitch of the output geometry
 };
 
 struct ConvEpi {
@@ -238,7 +240,10 @@ struct ConvEpi {
             orow = static_cast<long long>(n_img) * p.g.H * p.g.W + y * p.g.W + x;
         } else if (p.out_mode == OUT_WINDOW) {
             valid = valid && y >= p.wy0 && y < p.wy0 + p.wh && x >= p.wx0 && x < p.wx0 + p.ww;
-            orow = static_cast<long long>(n_img) * (p.wh + 1) * (p.ww + 1) + (y - p.wy0) * (p.ww + 1) + (x - p.wx0);
+            orow = static_cast<long long>(n_img) * p.ohp * p.owp + (y - p.wy0) * p.owp + (x - p.wx0);
+        } else if (p.out_mode == OUT_WINDOW_DENSE) {
+            valid = valid && y >= p.wy0 && y < p.wy0 + p.wh && x >= p.wx0 && x < p.wx0 + p.ww;
+            orow = static_cast<long long>(n_img) * p.wh * p.ww + (y - p.wy0) * p.ww + (x - p.wx0);
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {

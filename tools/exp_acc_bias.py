@@ -19,7 +19,8 @@ for taps, cpad, bn in ((1, 256, 256), (9, 128, 128), (9, 256, 256), (25, 64, 128
         shifts = [0] * taps
         out = torch.zeros(M, N, device="cuda")
         sh = torch.tensor(shifts, dtype=torch.int32)
-        _lib.check(lib.dfsfm_debug_gemm(_lib.ptr(split(a).cuda()), rows, cpad, _lib.ptr(split(w).cuda()), N, taps,
+        a_d, w_d = split(a).cuda(), split(w).cuda()  # keep alive until the launch has run
+        _lib.check(lib.dfsfm_debug_gemm(_lib.ptr(a_d), rows, cpad, _lib.ptr(w_d), N, taps,
                                         ctypes.c_void_p(sh.data_ptr()), cpad, bn, sp, _lib.ptr(out), M, N, None))
         torch.cuda.synchronize()
         ref = ref_gemm(a, w, shifts, cpad, M, N)
