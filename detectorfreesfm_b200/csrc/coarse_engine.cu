@@ -261,7 +261,7 @@ void CoarseEngine::ensure_tok(int n) {
 void CoarseEngine::kv_state(int side, int n, cudaStream_t st) {
     const int chunks = (n + kKvTokPerCta - 1) / kKvTokPerCta;
     kv_partial_kernel<32><<<dim3(chunks, 1), 256, 0, st>>>(tok_.qkv[side] + 256, tok_.qkv[side] + 512, 768, tok_.seg_dev + side, chunks,
-                                                            tok_.kv_part);
+                                                            tok_.kv_part, kKvTokPerCta);
     count_launch();
     kv_final_kernel<32><<<1, 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + side, chunks, tok_.kv_state);
     count_launch();

@@ -83,7 +83,8 @@ constexpr int kKvTokPerCta = 128;
 // grid (chunks, segments); block = 8 heads * D threads.  part: [seg][chunk][8*D*(D+1)]
 template <int D>
 static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* __restrict__ K, const float* __restrict__ V, int ld,
-                                                            const Seg* __restrict__ segs, int max_chunks, float* __restrict__ part) {
+                                                            const Seg* __restrict__ segs, int max_chunks, float* __restrict__ part,
+                                                            int tok_per_cta) {
     constexpr int C = 8 * D;
     constexpr int SUB = 16;
     __shared__ float Ks[SUB][C];
@@ -96,8 +97,8 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     for (int v = 0; v < D; ++v) acc[v] = 0.f;
     float ksum = 0.f;
     const float len = static_cast<float>(sg.count);
-    const int t0 = blockIdx.x * kKvTokPerCta;
-    const int t1 = min(t0 + kKvTokPerCta, sg.valid);
+    const int t0 = blockIdx.x * tok_per_cta;
+    const int t1 = min(t0 + tok_per_cta, sg.valid);
     for (int tb = t0; tb < t1; tb += SUB) {
         const int nt = min(SUB, t1 - tb);
         __syncthreads();

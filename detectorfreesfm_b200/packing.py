@@ -101,3 +101,52 @@ def position_encoding(h, w, d_model=256):
     pe[2::4] = torch.sin(y_position * div_term)
     pe[3::4] = torch.cos(y_position * div_term)
     return pe.flatten(1).t().contiguous()
+
+
+VGG_CONVS = ((0, "c11"), (2, "c12"), (5, "c21"), (7, "c22"), (10, "c31"), (12, "c32"), (14, "c33"))
+
+
+def pack_multiview(sd):
+    """MultiviewMatcher checkpoint -> engine parameters for dfsfm_refine_set_param.  Accepts the keys after
+    multiview_match_worker.py:42-52 (``matcher.`` stripped, loftr_fine -> fine_transformer) or the raw checkpoint keys."""
+    fixed = {}
+    for k, v in sd.items():
+        if k.startswith("matcher."):
+            k = k[len("matcher."):]
+        if "loftr_coarse" in k:
+            continue
+        fixed[k.replace("loftr_fine", "fine_transformer")] = v
+    sd = fixed
+    out = {}
+
+    def put(name, t, kind):
+        t = t.float().contiguous()
+        if t.dim() == 1:
+            t = t.view(1, -1)
+        out[name] = (t, kind)
+
+    for idx, name in VGG_CONVS:
+        w = sd[f"backbone.encoder.{idx}.weight"]
+        b = sd[f"backbone.encoder.{idx}.bias"]
+        if name == "c11":
+            put("c11.w", w.reshape(64, 27), 1)   # [cout][cin*3*3] for the fused RoIAlign + conv1_1 kernel
+        else:
+            put(name + ".w", conv_matrix(w), 0)
+        put(name + ".b", b, 1)
+    for i in range(2):
+        a = f"backbone.adaptation_layers.adap_layer_{i}"
+        put(f"a{i}.0.w", conv_matrix(sd[a + ".0.weight"]), 0)
+        put(f"a{i}.0.b", sd[a + ".0.bias"], 1)
+        s, b = _fold_bn(sd, a + ".3")
+        put(f"a{i}.2.w", conv_matrix(sd[a + ".2.weight"], s), 0)
+        put(f"a{i}.2.b", sd[a + ".2.bias"].double() * s + b, 1)
+    for i in range(4):
+        p = f"fine_transformer.layers.{i}"
+        put(f"tr.{i}.qkv", torch.cat([sd[p + ".q_proj.weight"], sd[p + ".k_proj.weight"], sd[p + ".v_proj.weight"]], 0), 0)
+        put(f"tr.{i}.merge", sd[p + ".merge.weight"], 0)
+        put(f"tr.{i}.mlp0", sd[p + ".mlp.0.weight"], 0)
+        put(f"tr.{i}.mlp2", sd[p + ".mlp.2.weight"], 0)
+        for n in ("1", "2"):
+            put(f"tr.{i}.ln{n}.g", sd[p + f".norm{n}.weight"], 1)
+            put(f"tr.{i}.ln{n}.b", sd[p + f".norm{n}.bias"], 1)
+    return out
