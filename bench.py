@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two DetectorFreeSfM hot paths on B200 (contract: task statement / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference's CPU path: the oracle port, bounded sample)
+
+One "step" = one pass of HP-1 over the demo-scene workload C2: 8 synthetic 832x832 images, exhaustive pairing = 28 image
+pairs, each pair -> (M,5) matches (BASELINE.json configs[1]).  `value` = image-pairs/s with the images resident in HBM and
+the backbone run for both images of every pair (exactly the work the reference does per pair); `e2e` = the same through the
+plugin call (B200LoFTR.forward on a dict) from pinned HOST images with the match arrays copied back.  `hp2` carries the second
+hot path: tracks/s of one refinement chunk (C3: 2000 tracks, <= 9 query views).  With N ranks every rank processes its own
+scene (weak scaling) and the per-pair match arrays are gathered to rank 0 inside the timed region.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from tests import util  # noqa: E402  (seeded synthetic inputs shared with the tests)
+
+HW = 832
+N_IMAGES = 8
+
+
+def conv_gemm_flops(H, W):
+    """Algorithmic FLOPs (2*MAC, true channel counts) of the backbone GEMM convolutions feeding x3_out for one HxW image
+    (ResNetFPN_8_2 coarse sub-graph without the 7x7 stem, resnet_fpn.py:100-108)."""
+    p2, p4, p8 = (H // 2) * (W // 2), (H // 4) * (W // 4), (H // 8) * (W // 8)
+    f = 4 * p2 * 9 * 128 * 128
+    f += p4 * (9 * 128 * 196 + 9 * 196 * 196 + 128 * 196 + 2 * 9 * 196 * 196)
+    f += p8 * (9 * 196 * 256 + 9 * 256 * 256 + 196 * 256 + 2 * 9 * 256 * 256 + 256 * 256)
+    return 2.0 * f
+
+
+def pair_flops(H, W):
+    L = (H // 8) * (W // 8)
+    stem = 2.0 * (H // 2) * (W // 2) * 128 * 49
+    backbone = 2 * (conv_gemm_flops(H, W) + stem)
+    transformer = 16 * L * 1.343e6
+    sim = 3 * 2.0 * L * L * 256       # two statistics passes + one confidence pass
+    return backbone + transformer + sim
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops": d["bf16_tflops_sustained"], "hbm": d["hbm_gbs"], "src": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+    return {"tflops": 1590.0, "hbm": 6650.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+def profile_report(lib):
+    n = lib.dfsfm_profile_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 16)
+    lib.dfsfm_profile_report(buf, n + 16)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        label, cnt, ms = line.split()
+        out[label] = (int(cnt), float(ms))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU implementation of HP-1 (the oracle port, validated bit-exact against the reference modules in
+    tests/test_oracle_vs_reference.py), all host threads, on a bounded sample: one 832x832 pair per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import loftr_oracle as lo
+    from oracle import weights
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = weights.loftr_state_dict(0)
+    im0, im1 = util.synth_image(HW, HW, 1000), util.synth_image(HW, HW, 1001)
+    data = {"image0": im0, "image1": im1, "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
+    for _ in range(min(args.warmup, 1)):
+        lo.loftr_forward(data, sd)
+    steps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        lo.loftr_forward(data, sd)
+    dt = time.perf_counter() - t0
+    v = steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "image-pairs/s coarse-match", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": f"C2 demo scene: LoFTR coarse_only pairs at {HW}x{HW}", "sample": "1 pair per step"},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"{steps} x one {HW}x{HW} pair, oracle/loftr_oracle.py (PyTorch CPU fp32)"},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--hp2-tracks", type=int, default=2000)
+    ap.add_argument("--skip-hp2", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher, _lib
+    from detectorfreesfm_b200 import dist as D
+    from oracle import weights
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.load_library()
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    # ------------------------------------------------------------------ HP-1 workload: one scene per rank
+    matcher = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=2 * N_IMAGES).cuda(local).eval()
+    matcher.load_state_dict(weights.loftr_state_dict(0))
+    host_images = [util.synth_image(HW, HW, 1000 * (rank + 1) + i).pin_memory() for i in range(N_IMAGES)]
+    dev_images = [im.to(dev) for im in host_images]
+    pairs = [(i, j) for i in range(N_IMAGES) for j in range(i + 1, N_IMAGES)]
+    ones = torch.ones(1, 2, device=dev)
+
+    def step_resident(cached):
+        """inputs resident in HBM; returns the per-pair (M,5) device arrays"""
+        matcher._cache.clear()
+        out = []
+        for (i, j) in pairs:
+            data = {"image0": dev_images[i], "image1": dev_images[j], "scale0": ones, "scale1": ones}
+            if cached:
+                data["pair_key"] = ((f"im{i}",), (f"im{j}",))
+            matcher(data)
+            out.append(torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1))
+        return out
+
+    h2d = d2h = 0
+
+    def step_e2e(cached):
+        """the plugin call from HOST buffers: pinned images -> device each pair, (M,5) match arrays back to the host"""
+        nonlocal h2d, d2h
+        matcher._cache.clear()
+        h2d = d2h = 0
+        res = []
+        for (i, j) in pairs:
+            a, b = host_images[i].to(dev, non_blocking=True), host_images[j].to(dev, non_blocking=True)
+            h2d += a.numel() * 4 + b.numel() * 4
+            data = {"image0": a, "image1": b, "scale0": ones, "scale1": ones}
+            if cached:
+                data["pair_key"] = ((f"im{i}",), (f"im{j}",))
+            matcher(data)
+            m = np.concatenate([data["mkpts0_f"].cpu().numpy(), data["mkpts1_f"].cpu().numpy(), data["mconf"].cpu().numpy()[:, None]], -1)
+            d2h += m.nbytes
+            res.append(m)
+        return res
+
+    def timed(fn, steps, gather):
+        D.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+            if gather and world > 1:
+                D.gather_varlen([o if torch.is_tensor(o) else torch.from_numpy(o).to(dev) for o in out])
+        e1.record()
+        torch.cuda.synchronize()
+        D.barrier()
+        return D.max_over_ranks(e0.elapsed_time(e1), dev)
+
+    for _ in range(W):
+        step_resident(False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = lib.dfsfm_launch_count()
+    ms_cold = timed(lambda: step_resident(False), K, True)
+    launches = lib.dfsfm_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_cached = timed(lambda: step_resident(True), K, True)
+    step_e2e(False)
+    ms_e2e = timed(lambda: step_e2e(False), K, True)
+    ms_e2e_cached = timed(lambda: step_e2e(True), K, True)
+    n_pairs = len(pairs) * world
+
+    # ------------------------------------------------------------------ roofline attribution of the dominant kernel
+    lib.dfsfm_profile_enable(1)
+    step_resident(False)
+    prof = profile_report(lib)
+    lib.dfsfm_profile_enable(0)
+    peaks = measured_peaks()
+    conv_cnt, conv_ms = prof.get("conv", (0, 0.0))
+    conv_alg = conv_gemm_flops(HW, HW) * 2 * len(pairs)
+    achieved = conv_alg / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
+    total_ms = sum(v[1] for v in prof.values())
+    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,split,ConvEpi> (backbone implicit-GEMM convolutions)",
+                "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
+                "traffic": None, "peak_source": peaks["src"],
+                "note": "achieved = algorithmic FLOPs (true channel counts, 1 pass); the kernel executes 3 fp16 MMA passes per K-step "
+                        "(split-fp16 operands for fp32-grade parity) => tensor-pipe utilisation = 3 x frac (+ padding)",
+                "launches": conv_cnt, "avg_launch_ms": conv_ms / conv_cnt if conv_cnt else None, "share_of_step": conv_ms / total_ms if total_ms else None,
+                "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items())}}
+
+    # ------------------------------------------------------------------ HP-2: one refinement chunk (C3)
+    hp2 = None
+    if not args.skip_hp2:
+        from tests.test_refine_gpu import multiview_config, to_cuda
+        rm = B200MultiviewMatcher(multiview_config(15, 7), test=True).cuda(local).eval()
+        rm.load_state_dict(weights.multiview_state_dict(0))
+        chunk = util.synth_chunk(M=args.hp2_tracks, n_img=10, max_views=9, hw=(600, 800), seed=11 + rank, scales=torch.ones(1, 10, 2))
+        host_imgs = [im.pin_memory() for im in chunk["images"]]
+        n_patches = int(chunk["track_valid_mask"].sum()) + args.hp2_tracks
+        cd = to_cuda(chunk)
+
+        def chunk_resident():
+            d = dict(cd)
+            rm(d)
+            return d
+
+        def chunk_e2e():
+            d = dict(cd)
+            d["images"] = [im.to(dev, non_blocking=True) for im in host_imgs]
+            rm(d)
+            return d["query_points_refined"].cpu(), d["reference_points_refined"][-1].cpu()
+
+        for _ in range(2):
+            chunk_resident()
+        k2 = max(2, min(K, 3))
+        ms2 = timed(chunk_resident, k2, False)
+        ms2_e2e = timed(chunk_e2e, k2, False)
+        lib.dfsfm_profile_enable(1)
+        chunk_resident()
+        prof2 = profile_report(lib)
+        lib.dfsfm_profile_enable(0)
+        pc_cnt, pc_ms = prof2.get("pconv", (0, 0.0))
+        # algorithmic FLOPs per patch of the GEMM convolutions as the reference executes them (1.024 GFLOP/patch
+        # incl. the 4.2 MFLOP conv1_1 which is a SIMT kernel here)
+        pconv_alg = n_patches * (1.024e9 - 2 * 35 * 35 * 27 * 64)
+        hp2 = {"metric": "tracks/s refinement", "value": args.hp2_tracks * k2 * world / (ms2 * 1e-3), "unit": "tracks/s",
+               "ms_per_chunk": ms2 / k2, "tracks_per_chunk": args.hp2_tracks, "patches_per_chunk": n_patches,
+               "e2e": {"value": args.hp2_tracks * k2 * world / (ms2_e2e * 1e-3), "unit": "tracks/s",
+                       "h2d_bytes_per_step": sum(im.numel() * 4 for im in host_imgs), "d2h_bytes_per_step": args.hp2_tracks * 2 * 4 * 10},
+               "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,split,ConvEpi> (S2DNet patch convolutions)",
+                            "achieved": pconv_alg / (pc_ms * 1e-3) / 1e12 if pc_ms else None, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": pconv_alg / (pc_ms * 1e-3) / 1e12 / peaks["tflops"] if pc_ms else None,
+                            "note": "algorithmic = FLOPs the reference executes (1.02 GFLOP/patch); the engine skips the part of the 5x5 "
+                                    "adapter outside the centre window and runs 3 fp16 passes",
+                            "kernel_ms_per_chunk": {k: round(v[1], 3) for k, v in sorted(prof2.items())}}}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        from oracle import loftr_oracle as lo
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = weights.loftr_state_dict(0)
+        data = {"image0": host_images[0], "image1": host_images[1], "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
+        t0 = time.perf_counter()
+        n_cpu = 0
+        while n_cpu < 2 and time.perf_counter() - t0 < 25:
+            lo.loftr_forward(data, sd)
+            n_cpu += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": n_cpu / dt, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{n_cpu} x one {HW}x{HW} pair of the workload, oracle/loftr_oracle.py (PyTorch CPU fp32, validated bit-exact vs the reference)"}
+
+    total_launches = int(D.sum_over_ranks(launches, dev))
+    if rank == 0:
+        value = n_pairs * K / (ms_cold * 1e-3)
+        line = {
+            "metric": "image-pairs/s coarse-match (hp2: tracks/s refinement)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": ms_cold / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split (fp32-grade), fp32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": f"C2 demo scene: {N_IMAGES} synthetic {HW}x{HW} images, exhaustive {len(pairs)} pairs per rank, LoFTR coarse_only, thr 0.2",
+                       "l2": "per-step working set (activations of one 832x832 image ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
+                       "backbone": "run for both images of every pair in `value`/`e2e` (as the reference does); *_cached keys use the exact per-image feature cache",
+                       "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays"},
+            "value_cached": n_pairs * K / (ms_cached * 1e-3),
+            "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "value_cached": n_pairs * K / (ms_e2e_cached * 1e-3)},
+            "gpu_launches": total_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "algorithmic_gflop_per_pair": pair_flops(HW, HW) / 1e9, "hp2": hp2,
+        }
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -134,7 +134,7 @@ void CoarseEngine::conv(const HL* ins, int n_in, GemmCore core, const std::strin
     DFSFM_CHECK(static_cast<long long>(core.num_taps) * core.cpad == w.C, "weight K does not match taps*cpad for " + wname);
     ep.M = core.M;
     ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
-    launch_gemm_counted<BN, true, ConvEpi>(maps, core, ep, ep.N, st);
+    launch_gemm_counted<BN, true, ConvEpi>(maps, core, ep, ep.N, st, "conv");
 }
 
 static ConvEpiParams epi_flat(const Geom& g, int N, const HL& out, bool relu, const HL* res) {
@@ -163,8 +163,8 @@ void CoarseEngine::features(const float* img, int H, int W, const float* pe, flo
     // conv1 + bn1 + relu (resnet_fpn.py:102)
     {
         dim3 grid((w.g2.W + kStemTW - 1) / kStemTW, (w.g2.H + kStemTH - 1) / kStemTH, 1);
-        stem_conv_kernel<<<grid, 128, 0, st>>>(img, H, W, params.vec("stem.w"), params.vec("stem.b"), w.a2.hi, w.a2.lo());
-        count_launch();
+        { LaunchScope ls("stem", st);
+          stem_conv_kernel<<<grid, 128, 0, st>>>(img, H, W, params.vec("stem.w"), params.vec("stem.b"), w.a2.hi, w.a2.lo()); }
         DFSFM_CUDA(cudaGetLastError());
     }
     GemmCore c;
@@ -260,11 +260,11 @@ void CoarseEngine::ensure_tok(int n) {
 // KV state of side `side` (n tokens): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
 void CoarseEngine::kv_state(int side, int n, cudaStream_t st) {
     const int chunks = (n + kKvTokPerCta - 1) / kKvTokPerCta;
-    kv_partial_kernel<32><<<dim3(chunks, 1), 256, 0, st>>>(tok_.qkv[side] + 256, tok_.qkv[side] + 512, 768, tok_.seg_dev + side, chunks,
-                                                            tok_.kv_part, kKvTokPerCta);
-    count_launch();
-    kv_final_kernel<32><<<1, 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + side, chunks, tok_.kv_state);
-    count_launch();
+    { LaunchScope ls("kv", st);
+      kv_partial_kernel<32><<<dim3(chunks, 1), 256, 0, st>>>(tok_.qkv[side] + 256, tok_.qkv[side] + 512, 768, tok_.seg_dev + side, chunks,
+                                                            tok_.kv_part, kKvTokPerCta); }
+    { LaunchScope ls("kv", st);
+      kv_final_kernel<32><<<1, 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + side, chunks, tok_.kv_state); }
     DFSFM_CUDA(cudaGetLastError());
 }
 
@@ -288,24 +288,24 @@ void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, f
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
             c.M = na; c.b_row0 = 0;
             e.M = na; e.N = 768; e.elu_cols = 512; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
-            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st);
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
         } else {
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
             c.M = na; c.b_row0 = 0;
             e.M = na; e.N = 256; e.elu_cols = 256; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
-            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st);
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st, "lin");
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[b], kBM);
             c.M = nb; c.b_row0 = 256;
             e.M = nb; e.N = 512; e.elu_cols = 256; e.out_f32 = tok_.qkv[b]; e.out_col0 = 256;
-            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st);
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
         }
     }
     kv_state(b, nb, st);
     {
         const int blocks = (na + 63) / 64;
-        attn_apply_kernel<32><<<dim3(blocks, 1), 256, 0, st>>>(tok_.qkv[a], 768, tok_.seg_dev + a, tok_.kv_state, tok_.msg[a].hi,
-                                                                tok_.msg[a].lo(), 256);
-        count_launch();
+        { LaunchScope ls("attn", st);
+          attn_apply_kernel<32><<<dim3(blocks, 1), 256, 0, st>>>(tok_.qkv[a], 768, tok_.seg_dev + a, tok_.kv_state, tok_.msg[a].hi,
+                                                                tok_.msg[a].lo(), 256); }
         DFSFM_CUDA(cudaGetLastError());
     }
     // merge + norm1
@@ -318,7 +318,7 @@ void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, f
         e.M = na; e.N = 256; e.mode = LIN_LN;
         e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
         e.out_hi = tok_.m1[a].hi; e.out_lo = tok_.m1[a].lo(); e.out_ld = 256;
-        launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st);
+        launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st, "lin");
     }
     // mlp.0 on cat[x, message] + relu
     {
@@ -330,7 +330,7 @@ void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, f
         memset(&e, 0, sizeof(e));
         e.M = na; e.N = 512; e.mode = LIN_RELU_HL;
         e.out_hi = tok_.hid[a].hi; e.out_lo = tok_.hid[a].lo(); e.out_ld = 512;
-        launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st);
+        launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st, "lin");
     }
     // mlp.2 + norm2 + residual
     {
@@ -345,14 +345,14 @@ void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, f
         e.resid = xa; e.resid_ld = 256;
         e.out_f32 = xa; e.out_f32_ld = 256;
         e.out_hi = tok_.x[a].hi; e.out_lo = tok_.x[a].lo(); e.out_ld = 256;
-        launch_gemm_counted<256, true, LinEpi>(maps, c3, e, 256, st);
+        launch_gemm_counted<256, true, LinEpi>(maps, c3, e, 256, st, "lin");
     }
 }
 
 static void split_rows(const float* in, long long rows, int C, const HL& out, cudaStream_t st) {
     const long long n4 = rows * C / 4;
-    split_rows_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(in, n4, out.hi, out.lo());
-    count_launch();
+    { LaunchScope ls("split", st);
+      split_rows_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(in, n4, out.hi, out.lo()); }
     DFSFM_CUDA(cudaGetLastError());
 }
 
@@ -399,10 +399,10 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         maps.b = make_tmap(tok_.x[o].hi, 256, n[o], tok_.x[o].plane_elems(), 256);
         c.M = n[side];
         e.M = n[side]; e.N = n[o]; e.mode = SIM_STATS; e.part = tok_.part;
-        launch_gemm_counted<256, true, SimEpi>(maps, c, e, n[o], st);
+        launch_gemm_counted<256, true, SimEpi>(maps, c, e, n[o], st, "sim");
         const int tiles = (n[o] + 255) / 256;
-        stats_merge_kernel<<<(n[side] + 255) / 256, 256, 0, st>>>(tok_.part, tiles, n[side], tok_.stat[side]);
-        count_launch();
+        { LaunchScope ls("stats_merge", st);
+          stats_merge_kernel<<<(n[side] + 255) / 256, 256, 0, st>>>(tok_.part, tiles, n[side], tok_.stat[side]); }
     }
     DFSFM_CUDA(cudaMemsetAsync(tok_.best[0], 0, static_cast<size_t>(L) * 8, st));
     DFSFM_CUDA(cudaMemsetAsync(tok_.best[1], 0, static_cast<size_t>(S) * 8, st));
@@ -414,10 +414,10 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         e.M = L; e.N = S; e.mode = SIM_CONF;
         e.row_stat = tok_.stat[0]; e.col_stat = tok_.stat[1]; e.thr = thr;
         e.row_best = tok_.best[0]; e.col_best = tok_.best[1]; e.conf_out = conf_out;
-        launch_gemm_counted<256, true, SimEpi>(maps, c, e, S, st);
+        launch_gemm_counted<256, true, SimEpi>(maps, c, e, S, st, "sim");
     }
-    match_select_kernel<<<1, 1024, 0, st>>>(tok_.best[0], tok_.best[1], L, w0c, w1c, border, capacity, i_ids, j_ids, mconf, n_matches);
-    count_launch();
+    { LaunchScope ls("select", st);
+      match_select_kernel<<<1, 1024, 0, st>>>(tok_.best[0], tok_.best[1], L, w0c, w1c, border, capacity, i_ids, j_ids, mconf, n_matches); }
     DFSFM_CUDA(cudaGetLastError());
 }
 

@@ -11,6 +11,23 @@ std::atomic<long long>& launch_counter() {
     return c;
 }
 
+// ------------------------------------------------------------------------------------------------ profiler
+namespace {
+struct ProfRec { std::string label; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+}  // namespace
+bool profiling_enabled() { return g_prof_on; }
+void prof_begin(const char* label, cudaStream_t st) {
+    ProfRec r;
+    r.label = label;
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+
 // ---------------------------------------------------------------------------------------------------------
 // TensorFlow-style crop_and_resize forward (the reference's L0 native op):
 //   third_party/RoIAlign.pytorch/roi_align/src/cuda/crop_and_resize_kernel.cu:10-82 (semantics),
@@ -28,15 +45,16 @@ __global__ void __launch_bounds__(256) crop_and_resize_kernel(const float* __res
     if (b_in < 0 || b_in >= batch) {  // the reference silently skips such boxes on the GPU (kernel.cu:36-39)
         return;
     }
-    const float height_scale = (ch > 1) ? (y2 - y1) * (ih - 1) / (ch - 1) : 0.f;
-    const float width_scale = (cw > 1) ? (x2 - x1) * (iw - 1) / (cw - 1) : 0.f;
+    const float height_scale = (ch > 1) ? __fdiv_rn(__fmul_rn(y2 - y1, ih - 1), ch - 1) : 0.f;
+    const float width_scale = (cw > 1) ? __fdiv_rn(__fmul_rn(x2 - x1, iw - 1), cw - 1) : 0.f;
     const float* img = image + static_cast<long long>(b_in) * depth * ih * iw;
     for (long long idx = threadIdx.x; idx < crop_elems; idx += blockDim.x) {
         const int x = static_cast<int>(idx % cw);
         const int y = static_cast<int>((idx / cw) % ch);
         const int d = static_cast<int>(idx / (static_cast<long long>(cw) * ch));
-        const float in_y = (ch > 1) ? y1 * (ih - 1) + y * height_scale : 0.5f * (y1 + y2) * (ih - 1);
-        const float in_x = (cw > 1) ? x1 * (iw - 1) + x * width_scale : 0.5f * (x1 + x2) * (iw - 1);
+        // explicit round-to-nearest mul/add (no FMA contraction): bit-identical to the reference's CPU op (gcc, SSE)
+        const float in_y = (ch > 1) ? __fadd_rn(__fmul_rn(y1, ih - 1), __fmul_rn(y, height_scale)) : 0.5f * (y1 + y2) * (ih - 1);
+        const float in_x = (cw > 1) ? __fadd_rn(__fmul_rn(x1, iw - 1), __fmul_rn(x, width_scale)) : 0.5f * (x1 + x2) * (iw - 1);
         float v = extrapolation;
         if (!(in_y < 0 || in_y > ih - 1 || in_x < 0 || in_x > iw - 1)) {
             const int top = static_cast<int>(floorf(in_y)), bottom = static_cast<int>(ceilf(in_y));
@@ -47,9 +65,9 @@ __global__ void __launch_bounds__(256) crop_and_resize_kernel(const float* __res
             const float tr = __ldg(p + static_cast<long long>(top) * iw + right);
             const float bl = __ldg(p + static_cast<long long>(bottom) * iw + left);
             const float br = __ldg(p + static_cast<long long>(bottom) * iw + right);
-            const float t = tl + (tr - tl) * x_lerp;
-            const float bt = bl + (br - bl) * x_lerp;
-            v = t + (bt - t) * y_lerp;
+            const float t = __fadd_rn(tl, __fmul_rn(tr - tl, x_lerp));
+            const float bt = __fadd_rn(bl, __fmul_rn(br - bl, x_lerp));
+            v = __fadd_rn(t, __fmul_rn(bt - t, y_lerp));
         }
         out[idx] = v;
     }
@@ -63,6 +81,35 @@ const char* dfsfm_last_error(void) { return dfsfm::g_last_error.c_str(); }
 int dfsfm_version(void) { return 1; }
 int64_t dfsfm_launch_count(void) { return dfsfm::launch_counter().load(); }
 
+void dfsfm_profile_enable(int on) {
+    dfsfm::g_prof_on = on != 0;
+    if (on) {
+        for (auto& r : dfsfm::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+        dfsfm::g_prof.clear();
+    }
+}
+// Writes "label count total_ms\n" lines (labels aggregated) into buf; returns the number of bytes needed.
+int dfsfm_profile_report(char* buf, int cap) {
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto& r : dfsfm::g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto& e = agg[r.label];
+            e.first += 1;
+            e.second += ms;
+        }
+    }
+    std::string out;
+    for (auto& kv : agg) out += kv.first + " " + std::to_string(kv.second.first) + " " + std::to_string(kv.second.second) + "\n";
+    if (buf && cap > 0) {
+        const int n = static_cast<int>(out.size()) < cap - 1 ? static_cast<int>(out.size()) : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return static_cast<int>(out.size()) + 1;
+}
+
 int dfsfm_crop_and_resize_forward(const float* image_dev, int batch, int depth, int image_h, int image_w, const float* boxes_dev,
                                   const int32_t* box_index_dev, int num_boxes, float extrapolation_value, int crop_h, int crop_w,
                                   float* crops_dev, void* stream) {
@@ -71,9 +118,9 @@ int dfsfm_crop_and_resize_forward(const float* image_dev, int batch, int depth, 
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         // crops.zero_() of the reference (crop_and_resize_gpu.cpp:42-43): boxes with an invalid index keep zeros
         DFSFM_CUDA(cudaMemsetAsync(crops_dev, 0, static_cast<size_t>(num_boxes) * depth * crop_h * crop_w * sizeof(float), st));
+        dfsfm::LaunchScope ls("roialign", st);
         dfsfm::crop_and_resize_kernel<<<num_boxes, 256, 0, st>>>(image_dev, batch, depth, image_h, image_w, boxes_dev, box_index_dev,
                                                                 extrapolation_value, crop_h, crop_w, crops_dev);
-        dfsfm::count_launch();
         DFSFM_CUDA(cudaGetLastError());
     });
 }

@@ -28,10 +28,28 @@ inline int guard(F&& f) {
     }
 }
 
+// Optional per-launch CUDA-event timing (dfsfm_profile_*): bench.py turns it on for a few extra steps to attribute device
+// time to kernel families; it is off in every timed region.
+bool profiling_enabled();
+void prof_begin(const char* label, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct LaunchScope {  // counts one kernel launch; brackets it with events when profiling
+    cudaStream_t st;
+    bool on;
+    LaunchScope(const char* label, cudaStream_t s) : st(s), on(profiling_enabled()) {
+        if (on) prof_begin(label, st);
+    }
+    ~LaunchScope() {
+        if (on) prof_end(st);
+        count_launch();
+    }
+};
+
 template <int BN, bool kSplit, class Epi>
-inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
+inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st,
+                                const char* label = "gemm") {
+    LaunchScope ls(label, st);
     launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
-    count_launch();
 }
 
 // Packed parameters on the device: GEMM operands as split-fp16 [rows][cols], everything else as fp32.

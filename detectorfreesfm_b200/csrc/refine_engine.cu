@@ -136,7 +136,7 @@ void RefineEngine::conv(const HL& in, const PGeom& g, long long P, int taps_k, i
     maps.b = make_tmap(w, BN);
     ep.M = c.M;
     ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
-    launch_gemm_counted<BN, true, ConvEpi>(maps, c, ep, ep.N, st);
+    launch_gemm_counted<BN, true, ConvEpi>(maps, c, ep, ep.N, st, "pconv");
 }
 
 // 4-layer multiview transformer on the flat token array (token-wise linears over all patches; attention per segment).
@@ -161,16 +161,16 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             set_k(c, 128);
             memset(&e, 0, sizeof(e));
             e.M = Ti; e.N = 384; e.mode = LIN_F32_ELU; e.elu_cols = 256; e.out_f32 = qkv_.p; e.out_f32_ld = 384;
-            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 384, st);
+            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 384, st, "lin");
         }
         // KV state of every segment (one CTA per segment: chunk size >= the longest segment)
-        kv_partial_kernel<16><<<dim3(1, n_segs), 128, 0, st>>>(qkv_.p + 128, qkv_.p + 256, 384, segs_self, 1, kvstate_.p, max_count);
-        count_launch();
+        { LaunchScope ls("kv", st);
+          kv_partial_kernel<16><<<dim3(1, n_segs), 128, 0, st>>>(qkv_.p + 128, qkv_.p + 256, 384, segs_self, 1, kvstate_.p, max_count); }
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.
-        attn_apply_kernel<16><<<dim3((max_count + 63) / 64, n_segs), 256, 0, st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
-                                                                                  msg_.b.hi, msg_.b.lo(), 128);
-        count_launch();
+        { LaunchScope ls("attn", st);
+          attn_apply_kernel<16><<<dim3((max_count + 63) / 64, n_segs), 256, 0, st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
+                                                                                  msg_.b.hi, msg_.b.lo(), 128); }
         DFSFM_CUDA(cudaGetLastError());
         {   // merge + norm1
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(msg_.b);
@@ -179,7 +179,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             memset(&e, 0, sizeof(e));
             e.M = Ti; e.N = 128; e.mode = LIN_LN; e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
             e.out_hi = m1_.b.hi; e.out_lo = m1_.b.lo(); e.out_ld = 128;
-            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st);
+            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st, "lin");
         }
         {   // mlp.0 on cat[x, message] + relu
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(i == 1 ? m1_.b : x_.b);
@@ -189,7 +189,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
             memset(&e, 0, sizeof(e));
             e.M = Ti; e.N = 256; e.mode = LIN_RELU_HL; e.out_hi = hid_.b.hi; e.out_lo = hid_.b.lo(); e.out_ld = 256;
-            launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 256, st);
+            launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 256, st, "lin");
         }
         {   // mlp.2 + norm2 + residual
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(hid_.b);
@@ -200,7 +200,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             e.M = Ti; e.N = 128; e.mode = LIN_LN; e.gamma = params.vec(p + ".ln2.g"); e.beta = params.vec(p + ".ln2.b");
             e.resid = xf_.p; e.resid_ld = 128; e.out_f32 = xf_.p; e.out_f32_ld = 128;
             e.out_hi = x_.b.hi; e.out_lo = x_.b.lo(); e.out_ld = 128;
-            launch_gemm_counted<128, true, LinEpi>(maps, c3, e, 128, st);
+            launch_gemm_counted<128, true, LinEpi>(maps, c3, e, 128, st, "lin");
         }
     }
 }
@@ -299,16 +299,16 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
     DFSFM_CUDA(cudaMemsetAsync(d_std_.p, 0, static_cast<size_t>(Nq) * M * sizeof(float), st));
 
     // ---- S2DNet on patches (s2dnet.py:127-175)
-    patch_conv11_kernel<<<static_cast<unsigned>(P), 256, 0, st>>>(d_recs_.p, params.vec("c11.w"), params.vec("c11.b"), c11_.b.hi, c11_.b.lo(),
-                                                                 nullptr);
-    count_launch();
+    { LaunchScope ls("patch_conv11", st);
+      patch_conv11_kernel<<<static_cast<unsigned>(P), 256, 0, st>>>(d_recs_.p, params.vec("c11.w"), params.vec("c11.b"), c11_.b.hi, c11_.b.lo(),
+                                                                 nullptr); }
     DFSFM_CUDA(cudaGetLastError());
     { ConvEpiParams e = epi(g35_, 64, true); set_out(e, c12_.b); conv<64>(c11_.b, g35_, P, 3, 64, "c12", e, st); }
     auto pool = [&](const HL& in, const PGeom& gi, const HL& out, const PGeom& go, int C) {
         const long long total = P * go.H * go.W * (C / 8);
-        maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in.hi, in.lo(), gi.H, gi.W, C, out.hi, out.lo(), go.H, go.W,
-                                                                                     total);
-        count_launch();
+        { LaunchScope ls("pool", st);
+          maxpool3s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(in.hi, in.lo(), gi.H, gi.W, C, out.hi, out.lo(), go.H, go.W,
+                                                                                     total); }
         DFSFM_CUDA(cudaGetLastError());
     };
     pool(c12_.b, g35_, p1_.b, g18_, 64);
@@ -346,8 +346,8 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
         e.out_f32 = a1out_.p; e.out_f32_ld = 128;
         conv<128>(a1_.b, ga1_, P, 5, 64, "a1.2", e, st);
     }
-    bicubic_merge_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(a0out_.p, a1out_.p, ga1_.Wp, tab_, W_, xf_.p, x_.b.hi, x_.b.lo());
-    count_launch();
+    { LaunchScope ls("bicubic", st);
+      bicubic_merge_kernel<<<static_cast<unsigned>(P), 128, 0, st>>>(a0out_.p, a1out_.p, ga1_.Wp, tab_, W_, xf_.p, x_.b.hi, x_.b.lo()); }
     DFSFM_CUDA(cudaGetLastError());
 
     transformer(T, 2 * M, max_count, st);
@@ -361,8 +361,8 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
             DFSFM_CUDA(cudaFuncSetAttribute(fine_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             configured = true;
         }
-        fine_match_kernel<<<M, kFmThreads, smem, st>>>(xf_.p, d_tracks_.p, d_views_.p, Nq, W_, LW_, d_query_.p, d_ref_.p, d_std_.p, M);
-        count_launch();
+        { LaunchScope ls("finematch", st);
+          fine_match_kernel<<<M, kFmThreads, smem, st>>>(xf_.p, d_tracks_.p, d_views_.p, Nq, W_, LW_, d_query_.p, d_ref_.p, d_std_.p, M); }
         DFSFM_CUDA(cudaGetLastError());
     }
     DFSFM_CUDA(cudaMemcpyAsync(query_refined, d_query_.p, static_cast<size_t>(M) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -24,14 +24,15 @@ static __global__ void __launch_bounds__(256) patch_conv11_kernel(const PatchRec
     const PatchRec r = recs[blockIdx.x];
     for (int i = threadIdx.x; i < 3 * (kCrop + 2) * (kCrop + 3); i += 256) (&tile[0][0][0])[i] = 0.f;
     __syncthreads();
-    const float height_scale = (r.y2 - r.y1) * (r.H - 1) / (kCrop - 1);
-    const float width_scale = (r.x2 - r.x1) * (r.W - 1) / (kCrop - 1);
+    // explicit round-to-nearest mul/add/div (no FMA contraction): bit-identical to the reference's CPU op
+    const float height_scale = __fdiv_rn(__fmul_rn(r.y2 - r.y1, r.H - 1), kCrop - 1);
+    const float width_scale = __fdiv_rn(__fmul_rn(r.x2 - r.x1, r.W - 1), kCrop - 1);
     const float mean[3] = {0.485f, 0.456f, 0.406f};
     const float stdv[3] = {0.229f, 0.224f, 0.225f};
     for (int i = threadIdx.x; i < 3 * kCrop * kCrop; i += 256) {
         const int x = i % kCrop, y = (i / kCrop) % kCrop, d = i / (kCrop * kCrop);
-        const float in_y = r.y1 * (r.H - 1) + y * height_scale;
-        const float in_x = r.x1 * (r.W - 1) + x * width_scale;
+        const float in_y = __fadd_rn(__fmul_rn(r.y1, r.H - 1), __fmul_rn(y, height_scale));
+        const float in_x = __fadd_rn(__fmul_rn(r.x1, r.W - 1), __fmul_rn(x, width_scale));
         float v = 0.f;  // extrapolation_value
         if (!(in_y < 0 || in_y > r.H - 1 || in_x < 0 || in_x > r.W - 1)) {
             const int top = static_cast<int>(floorf(in_y)), bottom = static_cast<int>(ceilf(in_y));
@@ -40,9 +41,9 @@ static __global__ void __launch_bounds__(256) patch_conv11_kernel(const PatchRec
             const float* p = r.image + static_cast<long long>(d) * r.H * r.W;
             const float tl = __ldg(p + static_cast<long long>(top) * r.W + left), tr = __ldg(p + static_cast<long long>(top) * r.W + right);
             const float bl = __ldg(p + static_cast<long long>(bottom) * r.W + left), br = __ldg(p + static_cast<long long>(bottom) * r.W + right);
-            const float t = tl + (tr - tl) * x_lerp;
-            const float b = bl + (br - bl) * x_lerp;
-            v = t + (b - t) * y_lerp;
+            const float t = __fadd_rn(tl, __fmul_rn(tr - tl, x_lerp));
+            const float b = __fadd_rn(bl, __fmul_rn(br - bl, x_lerp));
+            v = __fadd_rn(t, __fmul_rn(b - t, y_lerp));
         }
         if (patches_out) patches_out[static_cast<long long>(blockIdx.x) * 3 * kCrop * kCrop + i] = v;
         tile[d][y + 1][x + 1] = (v - mean[d]) / stdv[d];

@@ -1,0 +1,62 @@
+"""Pin the oracle restatement against the UNMODIFIED reference modules imported from /root/reference (build container
+only; skipped on the GPU box where that tree does not exist -- the committed golden fixtures cover it there)."""
+import pytest
+import torch
+
+from oracle import ref_shims
+
+pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="/root/reference not present")
+
+
+def test_loftr_coarse_and_fine_match_reference():
+    from oracle import loftr_oracle as lo
+    from oracle import weights
+    from tests import util
+    LoFTR, _ = ref_shims.import_loftr()
+    sd = weights.loftr_state_dict(0)
+    for fine in (False, True):
+        m = LoFTR(ref_shims.loftr_config(thr=0.0, fine=fine, temperature=0.01)).eval()
+        m.load_state_dict(sd, strict=True)
+        im0, im1 = util.synth_pair(64, 96, seed=3)
+        d = {"image0": im0, "image1": im1, "scale0": torch.tensor([[1.5, 1.25]]), "scale1": torch.tensor([[1.0, 2.0]])}
+        with torch.no_grad():
+            m(d)
+        out = lo.loftr_forward({k: d[k] for k in ("image0", "image1", "scale0", "scale1")}, sd,
+                               {"thr": 0.0, "temperature": 0.01, "fine_enable": fine}, keep=True)
+        assert (d["conf_matrix"] - out["conf_matrix"]).abs().max().item() < 1e-6
+        assert torch.equal(d["i_ids"], out["i_ids"]) and torch.equal(d["j_ids"], out["j_ids"])
+        assert (d["mconf"] - out["mconf"]).abs().max().item() < 1e-6
+        assert (d["mkpts0_f"] - out["mkpts0_f"]).abs().max().item() < 1e-3
+        assert (d["mkpts1_f"] - out["mkpts1_f"]).abs().max().item() < 1e-3
+
+
+def test_multiview_matches_reference():
+    from oracle import multiview_oracle as mo
+    from oracle import weights
+    from tests import util
+    MM = ref_shims.import_multiview()
+    sd = weights.multiview_state_dict(0)
+    m = MM(config=ref_shims.multiview_config(15, 7), test=True).eval()
+    m.load_state_dict(sd, strict=True)
+    data = util.synth_chunk(M=20, n_img=4, max_views=3, seed=9)
+    d2 = {k: (v.clone() if torch.is_tensor(v) else list(v)) for k, v in data.items()}
+    with torch.no_grad():
+        m(d2)
+    out = mo.multiview_forward(data, sd, 15, 7)
+    mask = data["track_valid_mask"]
+    assert (d2["query_points_refined"] - out["query_points_refined"]).abs().max().item() < 1e-4
+    assert (d2["reference_points_refined"][-1] - out["reference_points_refined"])[mask].abs().max().item() < 1e-3
+    assert (d2["std"][-1] - out["std"])[mask].abs().max().item() < 1e-4
+
+
+def test_c_roialign_matches_reference_cpp():
+    from oracle import build_native
+    ext = ref_shims.build_ref_roialign()
+    g = torch.Generator().manual_seed(0)
+    image = torch.rand(2, 3, 40, 56, generator=g)
+    nb = torch.rand(64, 4, generator=g) * 1.4 - 0.2
+    nb[:, 2:] = nb[:, :2] + torch.rand(64, 2, generator=g) * 0.6
+    bi = torch.randint(0, 2, (64,), generator=g, dtype=torch.int32)
+    crops = torch.zeros(1)
+    ext.forward(image, nb.contiguous(), bi, 0.0, 35, 35, crops)
+    assert torch.equal(build_native.roialign_forward(image, nb, bi, 35, 35), crops)
