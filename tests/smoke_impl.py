@@ -1,0 +1,39 @@
+"""__graft_entry__.smoke(): one small invocation of each hot path on cuda:0, checked against the CPU oracle."""
+import torch
+
+
+def run():
+    assert torch.cuda.is_available(), "smoke() needs a CUDA device"
+    from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher
+    from oracle import loftr_oracle as lo
+    from oracle import multiview_oracle as mo
+    from oracle import weights
+    from tests import util
+    from tests.test_refine_gpu import multiview_config, to_cuda
+
+    # HP-1: one 96x128 pair through the plugin interface
+    sd = weights.loftr_state_dict(0)
+    m = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.01)).cuda(0).eval()
+    m.load_state_dict(sd)
+    im0, im1 = util.synth_pair(96, 128, seed=1)
+    ref = lo.loftr_forward({"image0": im0, "image1": im1}, sd, {"thr": 0.2, "temperature": 0.01}, keep=True)
+    data = {"image0": im0.cuda(), "image1": im1.cuda(), "_return_conf_matrix": True}
+    m(data)
+    err = (data["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item()
+    assert err < 1e-3, f"confidence parity {err}"
+    assert torch.equal(data["i_ids"].cpu(), ref["i_ids"]) and torch.equal(data["j_ids"].cpu(), ref["j_ids"])
+    print(f"[smoke] HP-1 coarse match: {len(ref['i_ids'])} matches, max |dconf| = {err:.2e}")
+
+    # HP-2: one 16-track chunk
+    sdm = weights.multiview_state_dict(0)
+    chunk = util.synth_chunk(M=16, n_img=4, max_views=3, seed=4)
+    refm = mo.multiview_forward(chunk, sdm, 15, 7)
+    rm = B200MultiviewMatcher(multiview_config(15, 7), test=True).cuda(0).eval()
+    rm.load_state_dict(sdm)
+    d = to_cuda(chunk)
+    rm(d)
+    mask = chunk["track_valid_mask"]
+    dq = (d["query_points_refined"].cpu() - refm["query_points_refined"]).abs().max().item()
+    dr = (d["reference_points_refined"][-1].cpu() - refm["reference_points_refined"])[mask].abs().max().item()
+    assert dq < 1e-3 and dr < 0.1, (dq, dr)
+    print(f"[smoke] HP-2 refinement chunk: max |d query| = {dq:.2e} px, max |d refined| = {dr:.2e} px")
