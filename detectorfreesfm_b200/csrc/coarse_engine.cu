@@ -44,6 +44,8 @@ struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per si
     int cap = 0;
     HL x[2], msg[2], m1[2], hid[2];
     float* qkv[2] = {nullptr, nullptr};
+    float* xf = nullptr;       // joint fp32 token array (residual stream)
+    int kv_chunks = 0;
     float* kv_part = nullptr;
     float* kv_state = nullptr;
     Seg* seg_dev = nullptr;
@@ -80,8 +82,7 @@ class CoarseEngine {
 
     template <int BN>
     void conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st);
-    void layer_call(int li, bool self, int a, int na, int b, int nb, float* xa, cudaStream_t st);
-    void kv_state(int side, int n, cudaStream_t st);
+    void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st);
 };
 
 static ParityBuf parity_alloc(long long rows, int C) {
@@ -228,6 +229,8 @@ void CoarseEngine::free_tok(TokWs& w) {
         if (w.best[s]) cudaFree(w.best[s]);
         w.qkv[s] = nullptr; w.stat[s] = nullptr; w.best[s] = nullptr;
     }
+    if (w.xf) cudaFree(w.xf);
+    w.xf = nullptr;
     if (w.kv_part) cudaFree(w.kv_part);
     if (w.kv_state) cudaFree(w.kv_state);
     if (w.seg_dev) cudaFree(w.seg_dev);
@@ -249,130 +252,133 @@ void CoarseEngine::ensure_tok(int n) {
         DFSFM_CUDA(cudaMalloc(&tok_.stat[s], static_cast<size_t>(cap) * sizeof(float2)));
         DFSFM_CUDA(cudaMalloc(&tok_.best[s], static_cast<size_t>(cap) * sizeof(unsigned long long)));
     }
-    const int chunks = (cap + kKvTokPerCta - 1) / kKvTokPerCta;
-    DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(chunks) * 256 * 33 * sizeof(float)));
-    DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(256) * 33 * sizeof(float)));
-    DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 2 * sizeof(Seg)));
+    tok_.kv_chunks = (cap + kKvTokPerCta - 1) / kKvTokPerCta;
+    DFSFM_CUDA(cudaMalloc(&tok_.xf, static_cast<size_t>(cap) * 256 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(2) * tok_.kv_chunks * 256 * 33 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(2) * 256 * 33 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 8 * sizeof(Seg)));
     const int tiles = (cap + 255) / 256;
     DFSFM_CUDA(cudaMalloc(&tok_.part, static_cast<size_t>(tiles) * cap * sizeof(float2)));
 }
 
-// KV state of side `side` (n tokens): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
-void CoarseEngine::kv_state(int side, int n, cudaStream_t st) {
-    const int chunks = (n + kKvTokPerCta - 1) / kKvTokPerCta;
-    { LaunchScope ls("kv", st);
-      kv_partial_kernel<32><<<dim3(chunks, 1), 256, 0, st>>>(tok_.qkv[side] + 256, tok_.qkv[side] + 512, 768, tok_.seg_dev + side, chunks,
-                                                            tok_.kv_part, kKvTokPerCta); }
-    { LaunchScope ls("kv", st);
-      kv_final_kernel<32><<<1, 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + side, chunks, tok_.kv_state); }
-    DFSFM_CUDA(cudaGetLastError());
-}
-
-// One LoFTREncoderLayer.forward(x = side a, source = side b)  (transformer.py:35-58); xa = fp32 tokens of side a (updated in place).
-void CoarseEngine::layer_call(int li, bool self, int a, int na, int b, int nb, float* xa, cudaStream_t st) {
+// One LoFTREncoderLayer.forward (transformer.py:35-58) on the token rows [x0, x0+xn) of the joint token array (image 0 at rows
+// [0,L), image 1 at [L,L+S)).  `self`: source == x (both images in one call, two attention segments); otherwise the source
+// rows are [s0, s0+sn).  kv_segs / apply_segs index the 6-entry device table built in transformer().
+void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count,
+                              cudaStream_t st) {
     const std::string p = "tr." + std::to_string(li);
     GemmCore c;
     memset(&c, 0, sizeof(c));
     set_k(c, 256);
     conv_taps_s1(c, 1, 0);
     LinEpiParams e;
+    float* qkv = tok_.qkv[0];
+    float* xf = tok_.xf;
+    auto rows_map = [&](const HL& b, int r0, int n) { return make_tmap(b.hi + static_cast<long long>(r0) * b.C, b.C, n, b.plane_elems(), kBM); };
     // q/k/v projections (+ elu+1 feature map on q,k)
     {
         TmapPack maps;
-        const HL& wq = params.mat(p + ".qkv");
-        maps.b = make_tmap(wq, 256);
+        maps.b = make_tmap(params.mat(p + ".qkv"), 256);
         memset(&e, 0, sizeof(e));
         e.mode = LIN_F32_ELU;
         e.out_f32_ld = 768;
         if (self) {
-            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
-            c.M = na; c.b_row0 = 0;
-            e.M = na; e.N = 768; e.elu_cols = 512; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
+            c.M = xn; c.b_row0 = 0;
+            e.M = xn; e.N = 768; e.elu_cols = 512; e.out_f32 = qkv + static_cast<long long>(x0) * 768; e.out_col0 = 0;
             launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
         } else {
-            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[a], kBM);
-            c.M = na; c.b_row0 = 0;
-            e.M = na; e.N = 256; e.elu_cols = 256; e.out_f32 = tok_.qkv[a]; e.out_col0 = 0;
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
+            c.M = xn; c.b_row0 = 0;
+            e.M = xn; e.N = 256; e.elu_cols = 256; e.out_f32 = qkv + static_cast<long long>(x0) * 768; e.out_col0 = 0;
             launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st, "lin");
-            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[b], kBM);
-            c.M = nb; c.b_row0 = 256;
-            e.M = nb; e.N = 512; e.elu_cols = 256; e.out_f32 = tok_.qkv[b]; e.out_col0 = 256;
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], s0, sn);
+            c.M = sn; c.b_row0 = 256;
+            e.M = sn; e.N = 512; e.elu_cols = 256; e.out_f32 = qkv + static_cast<long long>(s0) * 768; e.out_col0 = 256;
             launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
         }
     }
-    kv_state(b, nb, st);
-    {
-        const int blocks = (na + 63) / 64;
+    {   // KV state(s): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
+        const int chunks = (max_count + kKvTokPerCta - 1) / kKvTokPerCta;
+        { LaunchScope ls("kv", st);
+          kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
+                                                                      kKvTokPerCta); }
+        { LaunchScope ls("kv", st);
+          kv_final_kernel<32><<<dim3((256 * 33 + 255) / 256, n_segs), 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
+                                                                                   tok_.kv_state, kKvTokPerCta); }
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<32><<<dim3(blocks, 1), 256, 0, st>>>(tok_.qkv[a], 768, tok_.seg_dev + a, tok_.kv_state, tok_.msg[a].hi,
-                                                                tok_.msg[a].lo(), 256); }
+          attn_apply_kernel<32><<<dim3((max_count + 63) / 64, n_segs), 256, 0, st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
+                                                                                    tok_.msg[0].hi, tok_.msg[0].lo(), 256); }
         DFSFM_CUDA(cudaGetLastError());
     }
+    c.M = xn; c.b_row0 = 0;
     // merge + norm1
     {
         TmapPack maps;
-        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.msg[a], kBM);
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.msg[0], x0, xn);
         maps.b = make_tmap(params.mat(p + ".merge"), 256);
-        c.M = na; c.b_row0 = 0;
         memset(&e, 0, sizeof(e));
-        e.M = na; e.N = 256; e.mode = LIN_LN;
+        e.M = xn; e.N = 256; e.mode = LIN_LN;
         e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
-        e.out_hi = tok_.m1[a].hi; e.out_lo = tok_.m1[a].lo(); e.out_ld = 256;
+        e.out_hi = tok_.m1[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.m1[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
         launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st, "lin");
     }
     // mlp.0 on cat[x, message] + relu
     {
         TmapPack maps;
-        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(i == 1 ? tok_.m1[a] : tok_.x[a], kBM);
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(i == 1 ? tok_.m1[0] : tok_.x[0], x0, xn);
         maps.b = make_tmap(params.mat(p + ".mlp0"), 256);
         GemmCore c2 = c;
         c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
         memset(&e, 0, sizeof(e));
-        e.M = na; e.N = 512; e.mode = LIN_RELU_HL;
-        e.out_hi = tok_.hid[a].hi; e.out_lo = tok_.hid[a].lo(); e.out_ld = 512;
+        e.M = xn; e.N = 512; e.mode = LIN_RELU_HL;
+        e.out_hi = tok_.hid[0].hi + static_cast<long long>(x0) * 512; e.out_lo = tok_.hid[0].lo() + static_cast<long long>(x0) * 512; e.out_ld = 512;
         launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st, "lin");
     }
     // mlp.2 + norm2 + residual
     {
         TmapPack maps;
-        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.hid[a], kBM);
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.hid[0], x0, xn);
         maps.b = make_tmap(params.mat(p + ".mlp2"), 256);
         GemmCore c3 = c;
         set_k(c3, 512);
         memset(&e, 0, sizeof(e));
-        e.M = na; e.N = 256; e.mode = LIN_LN;
+        e.M = xn; e.N = 256; e.mode = LIN_LN;
         e.gamma = params.vec(p + ".ln2.g"); e.beta = params.vec(p + ".ln2.b");
-        e.resid = xa; e.resid_ld = 256;
-        e.out_f32 = xa; e.out_f32_ld = 256;
-        e.out_hi = tok_.x[a].hi; e.out_lo = tok_.x[a].lo(); e.out_ld = 256;
+        e.resid = xf + static_cast<long long>(x0) * 256; e.resid_ld = 256;
+        e.out_f32 = xf + static_cast<long long>(x0) * 256; e.out_f32_ld = 256;
+        e.out_hi = tok_.x[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.x[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
         launch_gemm_counted<256, true, LinEpi>(maps, c3, e, 256, st, "lin");
     }
 }
 
-static void split_rows(const float* in, long long rows, int C, const HL& out, cudaStream_t st) {
+static void split_rows(const float* in, long long rows, int C, __half* hi, __half* lo, cudaStream_t st) {
     const long long n4 = rows * C / 4;
-    { LaunchScope ls("split", st);
-      split_rows_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(in, n4, out.hi, out.lo()); }
+    LaunchScope ls("split", st);
+    split_rows_kernel<<<static_cast<unsigned>((n4 + 255) / 256), 256, 0, st>>>(in, n4, hi, lo);
     DFSFM_CUDA(cudaGetLastError());
 }
 
 void CoarseEngine::transformer(float* f0, int L, float* f1, int S, cudaStream_t st) {
-    ensure_tok(L > S ? L : S);
-    const Seg segs[2] = {{0, L, L, 0}, {0, S, S, 0}};
+    ensure_tok(L + S);
+    // joint token array: image 0 rows [0,L), image 1 rows [L,L+S); attention segments / KV-state slots:
+    //   [0],[1]: self (own state 0 / 1);  [2]: image 0 reading state 1;  [3]: image 1 reading state 0
+    const Seg segs[4] = {{0, L, L, 0}, {L, S, S, 1}, {0, L, L, 1}, {L, S, S, 0}};
     DFSFM_CUDA(cudaMemcpyAsync(tok_.seg_dev, segs, sizeof(segs), cudaMemcpyHostToDevice, st));
-    // the token planes have a fixed capacity; rows beyond L/S are never read by valid output rows
-    split_rows(f0, L, 256, tok_.x[0], st);
-    split_rows(f1, S, 256, tok_.x[1], st);
+    DFSFM_CUDA(cudaMemcpyAsync(tok_.xf, f0, static_cast<size_t>(L) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DFSFM_CUDA(cudaMemcpyAsync(tok_.xf + static_cast<long long>(L) * 256, f1, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    split_rows(tok_.xf, L + S, 256, tok_.x[0].hi, tok_.x[0].lo(), st);
+    const int mx = L > S ? L : S;
     for (int li = 0; li < 8; ++li) {
-        const bool self = (li % 2) == 0;  // layer_names = ['self','cross'] * 4 (default.py:22)
-        if (self) {
-            layer_call(li, true, 0, L, 0, L, f0, st);
-            layer_call(li, true, 1, S, 1, S, f1, st);
+        if ((li % 2) == 0) {  // layer_names = ['self','cross'] * 4 (default.py:22): both images in one pass
+            layer_call(li, true, 0, L + S, 0, L + S, 0, 2, 0, mx, st);
         } else {
-            layer_call(li, false, 0, L, 1, S, f0, st);  // feat0 attends feat1
-            layer_call(li, false, 1, S, 0, L, f1, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
+            layer_call(li, false, 0, L, L, S, 1, 1, 2, mx, st);  // feat0 attends feat1
+            layer_call(li, false, L, S, 0, L, 0, 1, 3, mx, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
         }
     }
+    DFSFM_CUDA(cudaMemcpyAsync(f0, tok_.xf, static_cast<size_t>(L) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DFSFM_CUDA(cudaMemcpyAsync(f1, tok_.xf + static_cast<long long>(L) * 256, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
 
 // ------------------------------------------------------------------------------------------------ matching
@@ -380,16 +386,16 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
                          int* i_ids, int* j_ids, float* mconf, int* n_matches, int capacity, float* conf_out, cudaStream_t st) {
     const int L = h0c * w0c, S = h1c * w1c;
     ensure_tok(L > S ? L : S);
-    split_rows(f0, L, 256, tok_.x[0], st);
-    split_rows(f1, S, 256, tok_.x[1], st);
+    split_rows(f0, L, 256, tok_.x[0].hi, tok_.x[0].lo(), st);
+    split_rows(f1, S, 256, tok_.x[1].hi, tok_.x[1].lo(), st);
     GemmCore c;
     memset(&c, 0, sizeof(c));
     set_k(c, 256);
     conv_taps_s1(c, 1, 0);
     SimEpiParams e;
     memset(&e, 0, sizeof(e));
-    e.scale = 1.f / 256.f;  // (f0 / sqrt(256)) . (f1 / sqrt(256))   (coarse_matching.py:103-104)
-    e.temperature = temperature;
+    // sim = (f0 / sqrt(256)) . (f1 / sqrt(256)) / temperature (coarse_matching.py:103-107), carried in the log2 domain
+    e.c2 = static_cast<float>(1.4426950408889634 / (256.0 * static_cast<double>(temperature)));
     const int n[2] = {L, S};
     // softmax statistics along both axes: rows of sim (dim=2) and rows of sim^T (dim=1)
     for (int side = 0; side < 2; ++side) {

@@ -431,18 +431,18 @@ struct LinEpi {
 };
 
 // ------------------------------------------------------------------- dual-softmax similarity epilogues
-// sim[i,j] = acc[i,j] * scale / temperature.   SIM_STATS: per-row (max, sum exp) over this CTA's BN columns, written
-// to part[blockIdx.y][row].  SIM_CONF: conf = softmax_row * softmax_col from finished row / column statistics; every
-// entry above thr competes for its row's and its column's best (64-bit atomicMax on (conf bits, ~index)).
+// t[i,j] = acc[i,j] * c2 with c2 = log2(e) / (d_model * temperature): the similarity in the log2 domain, so that every
+// exponential is one ex2.  SIM_STATS: per-row (max, sum 2^(t-max)) over this CTA's BN columns -> part[blockIdx.y][row].
+// SIM_CONF: conf = softmax_row * softmax_col = 2^(2t - rmax - cmax) / (rsum * csum) from finished row / column
+// statistics; every entry above thr competes for its row's and its column's best (64-bit atomicMax on (conf bits, ~index)).
 enum SimMode : int { SIM_STATS = 0, SIM_CONF = 1 };
 
 struct SimEpiParams {
     int M, N;       // rows (tokens of A), columns (tokens of B)
     int mode;
-    float scale;    // 1 / d_model
-    float temperature;
-    float2* part;   // SIM_STATS: [gridDim.y][M] (max, sumexp)
-    const float2* row_stat;  // SIM_CONF: [M] (max, sumexp)
+    float c2;       // log2(e) / (d_model * temperature)
+    float2* part;   // SIM_STATS: [gridDim.y][M] (max, sum) in the log2 domain
+    const float2* row_stat;  // SIM_CONF: [M] (max, 1/sum)
     const float2* col_stat;  // SIM_CONF: [N]
     float thr;
     unsigned long long* row_best;  // [M]
@@ -467,21 +467,22 @@ struct SimEpi {
                 float v[32];
                 load_acc32<kCorr>(tmem_warp + c0, v);
                 const int nb = n0 + c0;
+                if (nb >= p.N) continue;
                 float cm = -INFINITY;
+                if (nb + 32 <= p.N) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    v[j] = (nb + j < p.N) ? (v[j] * p.scale) / p.temperature : -INFINITY;
-                    cm = fmaxf(cm, v[j]);
-                }
-                if (cm > m) { s *= expf(m - cm); m = cm; }
-                if (m > -INFINITY) {
+                    for (int j = 0; j < 32; ++j) { v[j] *= p.c2; cm = fmaxf(cm, v[j]); }
+                } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) s += expf(v[j] - m);
+                    for (int j = 0; j < 32; ++j) { v[j] = (nb + j < p.N) ? v[j] * p.c2 : -INFINITY; cm = fmaxf(cm, v[j]); }
                 }
+                if (cm > m) { s *= exp2f(m - cm); m = cm; }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s += exp2f(v[j] - m);
             }
             if (valid) p.part[static_cast<long long>(blockIdx.y) * p.M + row] = make_float2(m, s);
         } else {
-            float2 rs = valid ? p.row_stat[row] : make_float2(0.f, 1.f);
+            const float2 rs = valid ? p.row_stat[row] : make_float2(0.f, 1.f);  // (max, 1/sum)
             float best = -1.f;
             int best_j = 0;
 #pragma unroll 1
@@ -493,9 +494,9 @@ struct SimEpi {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     if (nb + j < p.N) {
-                        const float sim = (v[j] * p.scale) / p.temperature;
+                        const float t = v[j] * p.c2;
                         const float2 cs = __ldg(p.col_stat + nb + j);
-                        const float conf = (expf(sim - rs.x) / rs.y) * (expf(sim - cs.x) / cs.y);
+                        const float conf = exp2f((t - rs.x) + (t - cs.x)) * (rs.y * cs.y);
                         if (p.conf_out) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
                         if (conf > p.thr) {
                             atomicMax(p.col_best + nb + j, pack_best(conf, row));

@@ -14,6 +14,7 @@
 namespace dfsfm {
 
 namespace {
+constexpr int kRefineKvTok = 256;
 struct PGeom {  // per-patch flat geometry
     int H, W, Hp, Wp;
     int rows() const { return Hp * Wp; }
@@ -70,7 +71,7 @@ class RefineEngine {
     BicubicTab tab_;
     HLBuf c11_, c12_, p1_, c21_, c22_, p2_, c31_, c32_, c33_, a0_, a1_;
     HLBuf x_, msg_, m1_, hid_;
-    DevBuf<float> a0out_, a1out_, xf_, qkv_, kvstate_, d_query_, d_ref_, d_std_;
+    DevBuf<float> a0out_, a1out_, xf_, qkv_, kvstate_, kvpart_, d_query_, d_ref_, d_std_;
     DevBuf<PatchRec> d_recs_;
     DevBuf<Seg> d_segs_;
     DevBuf<TrackRec> d_tracks_;
@@ -163,9 +164,14 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             e.M = Ti; e.N = 384; e.mode = LIN_F32_ELU; e.elu_cols = 256; e.out_f32 = qkv_.p; e.out_f32_ld = 384;
             launch_gemm_counted<128, true, LinEpi>(maps, c, e, 384, st, "lin");
         }
-        // KV state of every segment (one CTA per segment: chunk size >= the longest segment)
-        { LaunchScope ls("kv", st);
-          kv_partial_kernel<16><<<dim3(1, n_segs), 128, 0, st>>>(qkv_.p + 128, qkv_.p + 256, 384, segs_self, 1, kvstate_.p, max_count); }
+        // KV state of every segment: 256-token partials, then a fixed-order sum (deterministic)
+        {
+            const int chunks = (max_count + kRefineKvTok - 1) / kRefineKvTok;
+            { LaunchScope ls("kv", st);
+              kv_partial_kernel<16><<<dim3(chunks, n_segs), 128, 0, st>>>(qkv_.p + 128, qkv_.p + 256, 384, segs_self, chunks, kvpart_.p, kRefineKvTok); }
+            { LaunchScope ls("kv", st);
+              kv_final_kernel<16><<<dim3((8 * 16 * 17 + 255) / 256, n_segs), 256, 0, st>>>(kvpart_.p, segs_self, chunks, kvstate_.p, kRefineKvTok); }
+        }
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.
         { LaunchScope ls("attn", st);
@@ -289,6 +295,7 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
     a0out_.ensure(static_cast<size_t>(T) * 128); a1out_.ensure(static_cast<size_t>(P) * ga1_.rows() * 128);
     xf_.ensure(static_cast<size_t>(T) * 128); qkv_.ensure(static_cast<size_t>(T) * 384);
     kvstate_.ensure(static_cast<size_t>(2) * M * 8 * 16 * 17);
+    kvpart_.ensure(static_cast<size_t>(2) * M * ((max_count + kRefineKvTok - 1) / kRefineKvTok) * 8 * 16 * 17);
     d_query_.ensure(static_cast<size_t>(M) * 2); d_ref_.ensure(static_cast<size_t>(Nq) * M * 2); d_std_.ensure(static_cast<size_t>(Nq) * M);
     d_recs_.ensure(recs.size()); d_segs_.ensure(segs.size()); d_tracks_.ensure(tracks.size()); d_views_.ensure(views.size());
     DFSFM_CUDA(cudaMemcpyAsync(d_recs_.p, recs.data(), recs.size() * sizeof(PatchRec), cudaMemcpyHostToDevice, st));

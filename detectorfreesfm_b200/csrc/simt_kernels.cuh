@@ -79,7 +79,7 @@ struct Seg {
     int state;  // index of the KV state this segment writes / reads
 };
 
-constexpr int kKvTokPerCta = 128;
+constexpr int kKvTokPerCta = 64;
 // grid (chunks, segments); block = 8 heads * D threads.  part: [seg][chunk][8*D*(D+1)]
 template <int D>
 static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* __restrict__ K, const float* __restrict__ V, int ld,
@@ -121,17 +121,19 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     for (int v = 0; v < D; ++v) o[v] = acc[v];
     o[D] = ksum;
 }
-// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic)
+// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic).  grid (ceil(SZ/256), segments).
 template <int D>
-static __global__ void kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs, int max_chunks, float* __restrict__ state) {
+static __global__ void __launch_bounds__(256) kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs, int max_chunks,
+                                                              float* __restrict__ state, int tok_per_cta) {
     constexpr int SZ = 8 * D * (D + 1);
-    const Seg sg = segs[blockIdx.x];
-    const int nch = (sg.valid + kKvTokPerCta - 1) / kKvTokPerCta;
-    for (int i = threadIdx.x; i < SZ; i += blockDim.x) {
-        float s = 0.f;
-        for (int c = 0; c < nch; ++c) s += part[(static_cast<long long>(blockIdx.x) * max_chunks + c) * SZ + i];
-        state[static_cast<long long>(sg.state) * SZ + i] = s;
-    }
+    const Seg sg = segs[blockIdx.y];
+    const int nch = (sg.valid + tok_per_cta - 1) / tok_per_cta;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= SZ) return;
+    const float* p = part + static_cast<long long>(blockIdx.y) * max_chunks * SZ + i;
+    float s = 0.f;
+    for (int c = 0; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
+    state[static_cast<long long>(sg.state) * SZ + i] = s;
 }
 // grid (token blocks of 64, segments); block 256 = 8 warps; each warp handles 8 tokens.  lane -> (head-in-group, v).
 // Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
@@ -177,7 +179,7 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
 }
 
 // --------------------------------------------------------------------------------------------------------
-// merge per-column-tile softmax partials: stat[i] = (max, sum exp(. - max))
+// merge per-column-tile softmax partials (log2 domain): stat[i] = (max, sum 2^(. - max))
 static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T, int M, float2* __restrict__ stat) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
@@ -186,9 +188,9 @@ static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T
     float s = 0.f;
     for (int t = 0; t < T; ++t) {
         const float2 p = part[static_cast<long long>(t) * M + i];
-        s += p.y * expf(p.x - m);
+        s += p.y * exp2f(p.x - m);
     }
-    stat[i] = make_float2(m, s);
+    stat[i] = make_float2(m, 1.f / s);  // (max, 1 / sum): the confidence pass multiplies
 }
 
 // Mutual-nearest-neighbour selection + ordered compaction (CoarseMatching.get_coarse_match,
