@@ -130,7 +130,7 @@ void CoarseEngine::conv(const HL* ins, int n_in, GemmCore core, const std::strin
     const HL& w = params.mat(wname + ".w");
     TmapPack maps;
     for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(ins[i < n_in ? i : 0], kBM);
-    maps.b = make_tmap(w, BN);
+    maps.b = make_tmap(w, bbox(BN));
     core.b_row0 = 0;
     DFSFM_CHECK(static_cast<long long>(core.num_taps) * core.cpad == w.C, "weight K does not match taps*cpad for " + wname);
     ep.M = core.M;
@@ -278,7 +278,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     // q/k/v projections (+ elu+1 feature map on q,k)
     {
         TmapPack maps;
-        maps.b = make_tmap(params.mat(p + ".qkv"), 256);
+        maps.b = make_tmap(params.mat(p + ".qkv"), bbox(256));
         memset(&e, 0, sizeof(e));
         e.mode = LIN_F32_ELU;
         e.out_f32_ld = 768;
@@ -316,7 +316,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.msg[0], x0, xn);
-        maps.b = make_tmap(params.mat(p + ".merge"), 256);
+        maps.b = make_tmap(params.mat(p + ".merge"), bbox(256));
         memset(&e, 0, sizeof(e));
         e.M = xn; e.N = 256; e.mode = LIN_LN;
         e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
@@ -327,7 +327,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(i == 1 ? tok_.m1[0] : tok_.x[0], x0, xn);
-        maps.b = make_tmap(params.mat(p + ".mlp0"), 256);
+        maps.b = make_tmap(params.mat(p + ".mlp0"), bbox(256));
         GemmCore c2 = c;
         c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
         memset(&e, 0, sizeof(e));
@@ -339,7 +339,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.hid[0], x0, xn);
-        maps.b = make_tmap(params.mat(p + ".mlp2"), 256);
+        maps.b = make_tmap(params.mat(p + ".mlp2"), bbox(256));
         GemmCore c3 = c;
         set_k(c3, 512);
         memset(&e, 0, sizeof(e));
@@ -402,7 +402,7 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         const int o = 1 - side;
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[side].hi, 256, n[side], tok_.x[side].plane_elems(), kBM);
-        maps.b = make_tmap(tok_.x[o].hi, 256, n[o], tok_.x[o].plane_elems(), 256);
+        maps.b = make_tmap(tok_.x[o].hi, 256, n[o], tok_.x[o].plane_elems(), bbox(256));
         c.M = n[side];
         e.M = n[side]; e.N = n[o]; e.mode = SIM_STATS; e.part = tok_.part;
         launch_gemm_counted<256, true, SimEpi>(maps, c, e, n[o], st, "sim");
@@ -415,7 +415,7 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
     {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(tok_.x[0].hi, 256, L, tok_.x[0].plane_elems(), kBM);
-        maps.b = make_tmap(tok_.x[1].hi, 256, S, tok_.x[1].plane_elems(), 256);
+        maps.b = make_tmap(tok_.x[1].hi, 256, S, tok_.x[1].plane_elems(), bbox(256));
         c.M = L;
         e.M = L; e.N = S; e.mode = SIM_CONF;
         e.row_stat = tok_.stat[0]; e.col_stat = tok_.stat[1]; e.thr = thr;

@@ -11,6 +11,16 @@ std::atomic<long long>& launch_counter() {
     return c;
 }
 
+static int g_engine = -1;
+int engine_version() {
+    if (g_engine < 0) {
+        const char* e = getenv("DFSFM_ENGINE");
+        g_engine = (e && e[0] == '1') ? 1 : 2;
+    }
+    return g_engine;
+}
+void set_engine_version(int v) { g_engine = (v == 1) ? 1 : 2; }
+
 // ------------------------------------------------------------------------------------------------ profiler
 namespace {
 struct ProfRec { std::string label; cudaEvent_t a, b; };
@@ -81,6 +91,9 @@ const char* dfsfm_last_error(void) { return dfsfm::g_last_error.c_str(); }
 int dfsfm_version(void) { return 1; }
 int64_t dfsfm_launch_count(void) { return dfsfm::launch_counter().load(); }
 
+void dfsfm_set_engine(int version) { dfsfm::set_engine_version(version); }
+int dfsfm_get_engine(void) { return dfsfm::engine_version(); }
+
 void dfsfm_profile_enable(int on) {
     dfsfm::g_prof_on = on != 0;
     if (on) {
@@ -136,7 +149,7 @@ int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(a, C, a_rows, a_rows * C, kBM);
         const long long ktot = static_cast<long long>(taps) * cpad;
-        maps.b = make_tmap(w, static_cast<int>(ktot), w_rows, w_rows * ktot, bn);
+        maps.b = make_tmap(w, static_cast<int>(ktot), w_rows, w_rows * ktot, bbox(bn));
         GemmCore c;
         memset(&c, 0, sizeof(c));
         c.M = M;

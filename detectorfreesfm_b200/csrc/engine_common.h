@@ -45,11 +45,17 @@ struct LaunchScope {  // counts one kernel launch; brackets it with events when 
     }
 };
 
+// Engine selection: 2 = persistent CTA pairs (default), 1 = one CTA per tile.  DFSFM_ENGINE overrides (tests compare both).
+int engine_version();
+void set_engine_version(int v);
+inline int bbox(int bn) { return engine_version() == 2 ? bn / 2 : bn; }  // box rows of the weight tensor map
+
 template <int BN, bool kSplit, class Epi>
 inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st,
                                 const char* label = "gemm") {
     LaunchScope ls(label, st);
-    launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+    if (engine_version() == 2) launch_gemm2<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+    else launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
 }
 
 // Packed parameters on the device: GEMM operands as split-fp16 [rows][cols], everything else as fp32.

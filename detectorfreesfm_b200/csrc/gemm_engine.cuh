@@ -164,6 +164,162 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
     }
 }
 
+// ================================================================================================ engine v2
+// Persistent CTA-pair engine: a cluster of two CTAs (cta_group::2) owns a 256-row x BN output tile per step -- each CTA
+// stages its own 128 activation rows and HALF of the weight tile, the leader CTA issues M=256 tcgen05.mma for both, so the
+// shared-memory traffic per MMA drops from (A + B) to (A + B/2) per SM.  Clusters loop over tiles (static round-robin);
+// the TMA producer runs ahead across tile boundaries and, when TMEM has room for two accumulator sets (BN <= 128 with
+// split operands), the epilogue of tile i overlaps the MMAs of tile i+1.
+template <int BN, bool kSplit>
+struct Gemm2Cfg {
+    static constexpr int kABytes = kBM * 128;
+    static constexpr int kBBytes = (BN / 2) * 128;  // this CTA's half of the weight tile
+    static constexpr int kPlanes = kSplit ? 2 : 1;
+    static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
+    static constexpr int kBudget = 204 * 1024;
+    static constexpr int kStagesRaw = kBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    static constexpr int kCorrOff = kSplit ? kAccCols : 0;
+    static constexpr int kSetCols = kSplit ? 2 * kAccCols : kAccCols;
+    static constexpr int kAccStages = (512 / kSetCols) >= 2 ? 2 : 1;
+    static constexpr int kTmemCols = kSetCols * kAccStages;
+    static_assert(kStages >= 2, "tile too large");
+    static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256 && (BN / 2) % 8 == 0, "invalid UMMA N for a CTA pair");
+};
+
+template <int BN, bool kSplit, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
+                const int n_tiles) {
+    using Cfg = Gemm2Cfg<BN, kSplit>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
+        tma_prefetch_desc(&maps.b);
+        for (int s = 0; s < Cfg::kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+        }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int n_iters = core.num_taps * core.kchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+                const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
+                const int nrow = core.b_row0 + nt * BN + static_cast<int>(rank) * (BN / 2);
+                for (int it = 0; it < n_iters; ++it) {
+                    const int t = it / core.kchunks;
+                    const int c = it - t * core.kchunks;
+                    mbar_wait(&empty_bar[s], phase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
+                    uint8_t* st = smem + s * Cfg::kStageBytes;
+                    const CUtensorMap* am = &maps.a[core.tap_map[t]];
+                    const int row = m0 + core.tap_shift[t];
+                    const int kb = t * core.cpad + c * kBK;
+                    tma_load_3d_2sm(st, am, &full_bar[s], c * kBK, row, 0);
+                    if (kSplit) tma_load_3d_2sm(st + Cfg::kABytes, am, &full_bar[s], c * kBK, row, 1);
+                    uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
+                    tma_load_3d_2sm(sb, &maps.b, &full_bar[s], kb, nrow, 0);
+                    if (kSplit) tma_load_3d_2sm(sb + Cfg::kBBytes, &maps.b, &full_bar[s], kb, nrow, 1);
+                    if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * kBM, BN);
+            int s = 0;
+            uint32_t phase = 0;
+            int a = 0;
+            uint32_t aphase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(&tmem_empty_bar[a], aphase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_acc = tmem_base + a * Cfg::kSetCols;
+                const uint32_t tmem_corr = tmem_acc + Cfg::kCorrOff;
+                uint32_t acc = 0;
+                for (int it = 0; it < n_iters; ++it) {
+                    const int c = it % core.kchunks;
+                    mbar_wait(&full_bar[s], phase);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
+                    const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
+                    const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
+                    for (int k = 0; k < nk; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(a_hi + k * 32);
+                        const uint64_t db = make_smem_desc_sw128(b_hi + k * 32);
+                        umma_f16_2sm(tmem_acc, da, db, idesc, acc);
+                        if (kSplit) {
+                            const uint64_t dal = make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32);
+                            const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + k * 32);
+                            umma_f16_2sm(tmem_corr, da, dbl, idesc, acc);
+                            umma_f16_2sm(tmem_corr, dal, db, idesc, 1);
+                        }
+                        acc = 1;
+                    }
+                    umma_commit_2sm(&empty_bar[s]);
+                    if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
+                }
+                umma_commit_2sm(&tmem_full_bar[a]);
+                if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quad = warp & 3;
+        int a = 0;
+        uint32_t aphase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
+            const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
+            mbar_wait(&tmem_full_bar[a], aphase);
+            tc_fence_after();
+            Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
+                                                 nt * BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
+            if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ epilogues
 // 32 accumulator columns of this thread's row: main (+ correction accumulator, added with round-to-nearest).
 template <int kCorr>
@@ -383,7 +539,7 @@ struct LinEpi {
             if (p.mode == LIN_F32_ELU) {
                 if (nb < p.elu_cols) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : expm1f(v[j]) + 1.f;
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : expf(v[j]);  // elu(x) + 1 == exp(x) for x <= 0
                 }
             } else if (p.mode == LIN_RELU_HL) {
 #pragma unroll
@@ -480,7 +636,7 @@ struct SimEpi {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) s += exp2f(v[j] - m);
             }
-            if (valid) p.part[static_cast<long long>(blockIdx.y) * p.M + row] = make_float2(m, s);
+            if (valid) p.part[static_cast<long long>(n0 / BN) * p.M + row] = make_float2(m, s);
         } else {
             const float2 rs = valid ? p.row_stat[row] : make_float2(0.f, 1.f);  // (max, 1/sum)
             float best = -1.f;

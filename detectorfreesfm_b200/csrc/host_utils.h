@@ -102,6 +102,34 @@ inline void launch_gemm(const TmapPack& maps, const GemmCore& core, const typena
     DFSFM_CUDA(cudaGetLastError());
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        DFSFM_CUDA(cudaGetDevice(&dev));
+        DFSFM_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
+// engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
+template <int BN, bool kSplit, class Epi>
+inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
+    using Cfg = Gemm2Cfg<BN, kSplit>;
+    auto kern = gemm_tc2_kernel<BN, kSplit, Epi>;
+    static bool configured = false;
+    if (!configured) {
+        DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        configured = true;
+    }
+    const int m_pairs = (core.M + 2 * kBM - 1) / (2 * kBM);
+    const int n_tiles = (n_total + BN - 1) / BN;
+    const int tiles = m_pairs * n_tiles;
+    const int max_clusters = sm_count() / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    kern<<<dim3(2 * clusters), kGemmThreads, Cfg::kSmemBytes, st>>>(maps, core, ep, tiles, n_tiles);
+    DFSFM_CUDA(cudaGetLastError());
+}
+
 // Fill the tap table of a stride-1 k x k convolution on a flat-halo geometry with row pitch Wp.
 inline void conv_taps_s1(GemmCore& c, int k, int Wp) {
     const int r = k / 2;

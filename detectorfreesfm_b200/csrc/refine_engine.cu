@@ -134,7 +134,7 @@ void RefineEngine::conv(const HL& in, const PGeom& g, long long P, int taps_k, i
     a.rows = rows;  // the tensor map covers exactly the rows in use (OOB rows read as zero)
     CUtensorMap am = make_tmap(a.hi, a.C, rows, in.plane_elems(), kBM);
     for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = am;
-    maps.b = make_tmap(w, BN);
+    maps.b = make_tmap(w, bbox(BN));
     ep.M = c.M;
     ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
     launch_gemm_counted<BN, true, ConvEpi>(maps, c, ep, ep.N, st, "pconv");
@@ -158,7 +158,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         TmapPack maps;
         {   // q,k,v for every token (+ elu+1 on q,k)
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(x_.b);
-            maps.b = make_tmap(params.mat(p + ".qkv"), 128);
+            maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128));
             set_k(c, 128);
             memset(&e, 0, sizeof(e));
             e.M = Ti; e.N = 384; e.mode = LIN_F32_ELU; e.elu_cols = 256; e.out_f32 = qkv_.p; e.out_f32_ld = 384;
@@ -180,7 +180,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         DFSFM_CUDA(cudaGetLastError());
         {   // merge + norm1
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(msg_.b);
-            maps.b = make_tmap(params.mat(p + ".merge"), 128);
+            maps.b = make_tmap(params.mat(p + ".merge"), bbox(128));
             set_k(c, 128);
             memset(&e, 0, sizeof(e));
             e.M = Ti; e.N = 128; e.mode = LIN_LN; e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
@@ -189,7 +189,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         }
         {   // mlp.0 on cat[x, message] + relu
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(i == 1 ? m1_.b : x_.b);
-            maps.b = make_tmap(params.mat(p + ".mlp0"), 256);
+            maps.b = make_tmap(params.mat(p + ".mlp0"), bbox(256));
             GemmCore c2 = c;
             set_k(c2, 128);
             c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
@@ -199,7 +199,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         }
         {   // mlp.2 + norm2 + residual
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(hid_.b);
-            maps.b = make_tmap(params.mat(p + ".mlp2"), 128);
+            maps.b = make_tmap(params.mat(p + ".mlp2"), bbox(128));
             GemmCore c3 = c;
             set_k(c3, 256);
             memset(&e, 0, sizeof(e));

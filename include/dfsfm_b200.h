@@ -82,6 +82,9 @@ int dfsfm_refine_chunk(dfsfm_refine_t* h, int n_img, const float* const* images_
  * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */
 int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts,
                      int cpad, int bn, int split, float* out_dev, int M, int N, void* stream);
+/* GEMM engine variant: 2 = persistent CTA pairs (cta_group::2, default), 1 = one CTA per output tile.  Test hook. */
+void dfsfm_set_engine(int version);
+int dfsfm_get_engine(void);
 /* Per-launch CUDA-event timing for bench.py's roofline attribution: enable(1) clears and starts collecting, enable(0) stops;
  * report() synchronises the device and writes "label count total_ms" lines. Never on inside a timed region. */
 void dfsfm_profile_enable(int on);

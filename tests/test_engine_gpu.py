@@ -40,11 +40,23 @@ CASES = [
     (500, 256, 768, [0], 256, 256, 1, 500, 768),
     (400, 512, 256, [0], 512, 256, 1, 400, 256),
     (640, 64, 128, [sy * 21 + sx for sy in range(-2, 3) for sx in range(-2, 3)], 64, 128, 1, 640, 128),
+    # many tiles per cluster (persistent loop, accumulator ring) and an odd number of 128-row tiles
+    (128 * 331 + 17, 128, 128, [-3, 0, 5], 128, 128, 1, 128 * 331 + 17, 128),
+    (128 * 75, 256, 512, [0], 256, 256, 1, 128 * 75, 512),
+    (128 * 301, 64, 64, [0, 1], 64, 64, 0, 128 * 301, 64),
 ]
 
 
+@pytest.fixture(params=[1, 2], ids=["engine1", "engine2-cta-pairs"])
+def engine(request, lib):
+    prev = lib.dfsfm_get_engine()
+    lib.dfsfm_set_engine(request.param)
+    yield request.param
+    lib.dfsfm_set_engine(prev)
+
+
 @pytest.mark.parametrize("rows,C,Nrows,shifts,cpad,bn,sp,M,N", CASES)
-def test_debug_gemm(lib, rows, C, Nrows, shifts, cpad, bn, sp, M, N):
+def test_debug_gemm(lib, engine, rows, C, Nrows, shifts, cpad, bn, sp, M, N):
     from detectorfreesfm_b200 import _lib
     g = torch.Generator().manual_seed(rows * 7 + C)
     a = torch.randn(rows, C, generator=g)
