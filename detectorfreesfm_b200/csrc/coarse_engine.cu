@@ -307,7 +307,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
           kv_final_kernel<32><<<dim3((256 * 33 + 255) / 256, n_segs), 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
                                                                                    tok_.kv_state, kKvTokPerCta); }
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<32><<<dim3((max_count + 63) / 64, n_segs), 256, 0, st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
+          attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, 0, st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
                                                                                     tok_.msg[0].hi, tok_.msg[0].lo(), 256); }
         DFSFM_CUDA(cudaGetLastError());
     }

@@ -170,7 +170,7 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
 // shared-memory traffic per MMA drops from (A + B) to (A + B/2) per SM.  Clusters loop over tiles (static round-robin);
 // the TMA producer runs ahead across tile boundaries and, when TMEM has room for two accumulator sets (BN <= 128 with
 // split operands), the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, bool kSplit>
+template <int BN, bool kSplit, bool kSepCorr = true>
 struct Gemm2Cfg {
     static constexpr int kABytes = kBM * 128;
     static constexpr int kBBytes = (BN / 2) * 128;  // this CTA's half of the weight tile
@@ -181,8 +181,11 @@ struct Gemm2Cfg {
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
     static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    static constexpr int kCorrOff = kSplit ? kAccCols : 0;
-    static constexpr int kSetCols = kSplit ? 2 * kAccCols : kAccCols;
+    // kSepCorr: hi*lo + lo*hi go to their own accumulator (long-K convolutions).  Short-K linears fold them into the main
+    // accumulator (truncation bias ~ -5.5e-9*K*3 relative: harmless at K <= 512), which leaves TMEM room for a second
+    // accumulator set even at BN = 256, so the epilogue of a tile overlaps the MMAs of the next.
+    static constexpr int kCorrOff = (kSplit && kSepCorr) ? kAccCols : 0;
+    static constexpr int kSetCols = (kSplit && kSepCorr) ? 2 * kAccCols : kAccCols;
     static constexpr int kAccStages = (512 / kSetCols) >= 2 ? 2 : 1;
     static constexpr int kTmemCols = kSetCols * kAccStages;
     static_assert(kStages >= 2, "tile too large");
@@ -193,7 +196,7 @@ template <int BN, bool kSplit, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
                 const int n_tiles) {
-    using Cfg = Gemm2Cfg<BN, kSplit>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -282,7 +285,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                         if (kSplit) {
                             const uint64_t dal = make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32);
                             const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + k * 32);
-                            umma_f16_2sm(tmem_corr, da, dbl, idesc, acc);
+                            umma_f16_2sm(tmem_corr, da, dbl, idesc, Epi::kSeparateCorr ? acc : 1u);
                             umma_f16_2sm(tmem_corr, dal, db, idesc, 1);
                         }
                         acc = 1;
@@ -373,6 +376,7 @@ struct ConvEpiParams {
 
 struct ConvEpi {
     using Params = ConvEpiParams;
+    static constexpr bool kSeparateCorr = true;
     template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;
@@ -504,31 +508,27 @@ struct LinEpiParams {
 
 struct LinEpi {
     using Params = LinEpiParams;
+    static constexpr bool kSeparateCorr = false;
     template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         float mean = 0.f, rstd = 0.f;
         if (p.mode == LIN_LN) {
-            // two passes over this thread's TMEM row (BN == N == d_model): mean, then variance
-            float s = 0.f;
+            // one statistics pass over this thread's TMEM row (BN == N == d_model): shifted sums about the first element
+            float s1 = 0.f, s2 = 0.f, pivot = 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 float v[32];
                 load_acc32<kCorr>(tmem_warp + c0, v);
+                if (c0 == 0) pivot = v[0];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s += v[j];
+                for (int j = 0; j < 32; ++j) { const float d = v[j] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
             }
-            mean = s / static_cast<float>(BN);
-            float q = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                load_acc32<kCorr>(tmem_warp + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; q += d * d; }
-            }
-            rstd = rsqrtf(q / static_cast<float>(BN) + 1e-5f);
+            const float inv_n = 1.f / static_cast<float>(BN);
+            const float md = s1 * inv_n;
+            mean = pivot + md;
+            rstd = rsqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
         }
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -612,6 +612,7 @@ __device__ __forceinline__ unsigned long long pack_best(float conf, int idx) {
 
 struct SimEpi {
     using Params = SimEpiParams;
+    static constexpr bool kSeparateCorr = false;
     template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
         const int row = row0 + lane;

@@ -114,7 +114,7 @@ inline int sm_count() {
 // engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
 template <int BN, bool kSplit, class Epi>
 inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
-    using Cfg = Gemm2Cfg<BN, kSplit>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr>;
     auto kern = gemm_tc2_kernel<BN, kSplit, Epi>;
     static bool configured = false;
     if (!configured) {

@@ -175,7 +175,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<16><<<dim3((max_count + 63) / 64, n_segs), 256, 0, st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
+          attn_apply_kernel<16><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, 0, st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
                                                                                   msg_.b.hi, msg_.b.lo(), 128); }
         DFSFM_CUDA(cudaGetLastError());
         {   // merge + norm1

@@ -80,15 +80,18 @@ struct Seg {
 };
 
 constexpr int kKvTokPerCta = 64;
-// grid (chunks, segments); block = 8 heads * D threads.  part: [seg][chunk][8*D*(D+1)]
+// grid (chunks, segments); block = 8 heads * D threads.  part: [seg][chunk][8*D*(D+1)].
+// 16-token sub-batches: float4 global loads are issued one sub-batch ahead (register prefetch) so that the
+// shared-memory outer-product loop of batch i runs under the loads of batch i+1.
 template <int D>
 static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* __restrict__ K, const float* __restrict__ V, int ld,
                                                             const Seg* __restrict__ segs, int max_chunks, float* __restrict__ part,
                                                             int tok_per_cta) {
     constexpr int C = 8 * D;
+    constexpr int C4 = C / 4;
     constexpr int SUB = 16;
-    __shared__ float Ks[SUB][C];
-    __shared__ float Vs[SUB][C];
+    __shared__ __align__(16) float Ks[SUB][C];
+    __shared__ __align__(16) float Vs[SUB][C];
     const Seg sg = segs[blockIdx.y];
     const int tid = threadIdx.x;
     const int h = tid / D;
@@ -99,21 +102,45 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     const float len = static_cast<float>(sg.count);
     const int t0 = blockIdx.x * tok_per_cta;
     const int t1 = min(t0 + tok_per_cta, sg.valid);
+    const int s0 = tid / C4, c4 = tid - s0 * C4;  // this thread stages tokens s0, s0+4, s0+8, s0+12 at columns [4*c4, 4*c4+4)
+    float4 rk[4], rv[4];
+    auto load = [&](int tb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = tb + s0 + 4 * j;
+            if (t < t1) {
+                const long long r = static_cast<long long>(sg.start + t) * ld + c4 * 4;
+                rk[j] = *reinterpret_cast<const float4*>(K + r);
+                rv[j] = *reinterpret_cast<const float4*>(V + r);
+            } else {
+                rk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                rv[j] = rk[j];
+            }
+        }
+    };
+    if (t0 < t1) load(t0);
     for (int tb = t0; tb < t1; tb += SUB) {
         const int nt = min(SUB, t1 - tb);
         __syncthreads();
-        for (int i = tid; i < nt * C; i += C) {
-            const int s = i / C, c = i - s * C;
-            const long long r = static_cast<long long>(sg.start + tb + s) * ld + c;
-            Ks[s][c] = K[r];
-            Vs[s][c] = V[r] / len;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            *reinterpret_cast<float4*>(&Ks[s0 + 4 * j][c4 * 4]) = rk[j];
+            *reinterpret_cast<float4*>(&Vs[s0 + 4 * j][c4 * 4]) = make_float4(rv[j].x / len, rv[j].y / len, rv[j].z / len, rv[j].w / len);
         }
         __syncthreads();
+        if (tb + SUB < t1) load(tb + SUB);
         for (int s = 0; s < nt; ++s) {
             const float k = Ks[s][tid];
             ksum += k;
+            const float4* vp = reinterpret_cast<const float4*>(&Vs[s][h * D]);
 #pragma unroll
-            for (int v = 0; v < D; ++v) acc[v] = fmaf(k, Vs[s][h * D + v], acc[v]);
+            for (int v4 = 0; v4 < D / 4; ++v4) {
+                const float4 vv = vp[v4];
+                acc[4 * v4] = fmaf(k, vv.x, acc[4 * v4]);
+                acc[4 * v4 + 1] = fmaf(k, vv.y, acc[4 * v4 + 1]);
+                acc[4 * v4 + 2] = fmaf(k, vv.z, acc[4 * v4 + 2]);
+                acc[4 * v4 + 3] = fmaf(k, vv.w, acc[4 * v4 + 3]);
+            }
         }
     }
     float* o = part + (static_cast<long long>(blockIdx.y) * max_chunks + blockIdx.x) * (C * (D + 1)) + tid * (D + 1);
@@ -135,38 +162,52 @@ static __global__ void __launch_bounds__(256) kv_final_kernel(const float* __res
     for (int c = 0; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
     state[static_cast<long long>(sg.state) * SZ + i] = s;
 }
-// grid (token blocks of 64, segments); block 256 = 8 warps; each warp handles 8 tokens.  lane -> (head-in-group, v).
+// grid (token blocks of 32, segments); block 256 = 8 warps x 4 tokens.  lane + 32 j -> channel (head, d).
+// All q values of a warp's 4 tokens are loaded up front (C/8 independent coalesced loads per lane) before any use.
 // Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
+constexpr int kAttnTokPerCta = 32;
 template <int D>
 static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, int ldq, const Seg* __restrict__ segs,
                                                           const float* __restrict__ state, __half* __restrict__ out_hi,
                                                           __half* __restrict__ out_lo, int ldo) {
     constexpr int C = 8 * D;
     constexpr int SZ = C * (D + 1);
-    constexpr int HPW = 32 / D;  // heads handled per warp pass
+    constexpr int NJ = C / 32;  // channels per lane
+    constexpr int TPW = 4;
     __shared__ float st[SZ];
     const Seg sg = segs[blockIdx.y];
-    if (blockIdx.x * 64 >= sg.count) return;
+    if (blockIdx.x * kAttnTokPerCta >= sg.count) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tw = blockIdx.x * kAttnTokPerCta + warp * TPW;
+    float q[TPW][NJ];
+#pragma unroll
+    for (int ti = 0; ti < TPW; ++ti) {
+        const int t = tw + ti;
+        const bool ok = t < sg.valid;
+        const float* qp = Q + static_cast<long long>(sg.start + (ok ? t : 0)) * ldq + lane;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) q[ti][j] = ok ? __ldg(qp + 32 * j) : 0.f;
+    }
     for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
     __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int hs = lane / D, v = lane - hs * D;
+    const int hs = lane / D, v = lane - hs * D;  // D == 32: hs = 0, v = lane
     const float len = static_cast<float>(sg.count);
-    for (int ti = 0; ti < 8; ++ti) {
-        const int t = blockIdx.x * 64 + warp * 8 + ti;
+#pragma unroll
+    for (int ti = 0; ti < TPW; ++ti) {
+        const int t = tw + ti;
         if (t >= sg.count) break;
         const long long row = sg.start + t;
-        const bool tok_valid = t < sg.valid;
-        for (int hg = 0; hg < 8; hg += HPW) {
-            const int h = hg + hs;
-            const float q = tok_valid ? Q[row * ldq + h * D + v] : 0.f;  // here lane's "v" plays the role of d
-            float z = q * st[(h * D + v) * (D + 1) + D];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int h = (32 * j) / D + hs;
+            const float qq = q[ti][j];  // channel h*D + v: this lane's "v" plays the role of d
+            float z = qq * st[(h * D + v) * (D + 1) + D];
 #pragma unroll
             for (int o = D / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
             float acc = 0.f;
 #pragma unroll
             for (int d = 0; d < D; ++d) {
-                const float qd = __shfl_sync(0xffffffffu, q, hs * D + d);
+                const float qd = __shfl_sync(0xffffffffu, qq, hs * D + d);
                 acc = fmaf(qd, st[(h * D + d) * (D + 1) + v], acc);
             }
             const float r = acc * (1.f / (z + 1e-6f)) * len;
