@@ -58,7 +58,10 @@ struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per si
 
 class CoarseEngine {
   public:
-    explicit CoarseEngine(int device) : device_(device) { DFSFM_CUDA(cudaSetDevice(device)); }
+    explicit CoarseEngine(int device) : device_(device) {
+        DFSFM_CUDA(cudaSetDevice(device));
+        DFSFM_CUDA(cudaFuncSetAttribute(attn_apply_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<32>()));
+    }
     ~CoarseEngine() {
         for (auto& kv : feat_ws_) free_feat(kv.second);
         free_tok(tok_);
@@ -307,7 +310,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
           kv_final_kernel<32><<<dim3((256 * 33 + 255) / 256, n_segs), 256, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
                                                                                    tok_.kv_state, kKvTokPerCta); }
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, 0, st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
+          attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<32>(), st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
                                                                                     tok_.msg[0].hi, tok_.msg[0].lo(), 256); }
         DFSFM_CUDA(cudaGetLastError());
     }

@@ -50,6 +50,7 @@ class RefineEngine {
   public:
     RefineEngine(int device, int window, int left_window) : W_(window), LW_(left_window) {
         DFSFM_CUDA(cudaSetDevice(device));
+        DFSFM_CUDA(cudaFuncSetAttribute(attn_apply_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<16>()));
         DFSFM_CHECK(window % 2 == 1 && window >= 7 && window <= 15, "window must be odd, 7..15");
         DFSFM_CHECK(left_window % 2 == 1 && left_window >= 1 && left_window <= window, "left window must be odd and <= window");
         g35_ = PGeom{35, 35, 36, 36};
@@ -175,7 +176,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<16><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, 0, st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
+          attn_apply_kernel<16><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<16>(), st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
                                                                                   msg_.b.hi, msg_.b.lo(), 128); }
         DFSFM_CUDA(cudaGetLastError());
         {   // merge + norm1

@@ -162,59 +162,78 @@ static __global__ void __launch_bounds__(256) kv_final_kernel(const float* __res
     for (int c = 0; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
     state[static_cast<long long>(sg.state) * SZ + i] = s;
 }
-// grid (token blocks of 32, segments); block 256 = 8 warps x 4 tokens.  lane + 32 j -> channel (head, d).
-// All q values of a warp's 4 tokens are loaded up front (C/8 independent coalesced loads per lane) before any use.
+// grid (token blocks of 32, segments); block 256 = 8 warps x 4 tokens.  lane + 32 j -> output channel (head, v).
+// The warp's 4 query rows are staged in shared memory (coalesced float4 loads issued up front) and read back as broadcast
+// float4 -- per 16 FMAs the inner loop issues 4 state loads + 4 query loads instead of 16 + 16 shuffles.
 // Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
 constexpr int kAttnTokPerCta = 32;
+template <int D>
+constexpr int attn_smem_bytes() { return (8 * D * (D + 1) + 8 * 4 * 8 * D) * static_cast<int>(sizeof(float)); }
 template <int D>
 static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, int ldq, const Seg* __restrict__ segs,
                                                           const float* __restrict__ state, __half* __restrict__ out_hi,
                                                           __half* __restrict__ out_lo, int ldo) {
     constexpr int C = 8 * D;
     constexpr int SZ = C * (D + 1);
-    constexpr int NJ = C / 32;  // channels per lane
+    constexpr int NJ = C / 32;  // output channels per lane
     constexpr int TPW = 4;
-    __shared__ float st[SZ];
+    extern __shared__ __align__(16) float attn_sm[];
+    float* st = attn_sm;             // [C][D+1]: KV[h][d][v] at (h*D+d)*(D+1)+v, Ksum at +D
+    float* qs = attn_sm + SZ;        // [8 warps][TPW][C]
     const Seg sg = segs[blockIdx.y];
     if (blockIdx.x * kAttnTokPerCta >= sg.count) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tw = blockIdx.x * kAttnTokPerCta + warp * TPW;
-    float q[TPW][NJ];
-#pragma unroll
-    for (int ti = 0; ti < TPW; ++ti) {
-        const int t = tw + ti;
-        const bool ok = t < sg.valid;
-        const float* qp = Q + static_cast<long long>(sg.start + (ok ? t : 0)) * ldq + lane;
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) q[ti][j] = ok ? __ldg(qp + 32 * j) : 0.f;
+    float* qw = qs + warp * TPW * C;
+    {   // stage this warp's query rows (zeros for masked / out-of-range tokens)
+        constexpr int F4 = TPW * C / 4;
+        for (int i = lane; i < F4; i += 32) {
+            const int ti = i / (C / 4), c4 = i - ti * (C / 4);
+            const int t = tw + ti;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < sg.valid) v = *reinterpret_cast<const float4*>(Q + static_cast<long long>(sg.start + t) * ldq + c4 * 4);
+            *reinterpret_cast<float4*>(qw + ti * C + c4 * 4) = v;
+        }
     }
     for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
     __syncthreads();
     const int hs = lane / D, v = lane - hs * D;  // D == 32: hs = 0, v = lane
     const float len = static_cast<float>(sg.count);
+#pragma unroll 1
+    for (int j = 0; j < NJ; ++j) {
+        const int h = (32 * j) / D + hs;
+        float acc[TPW], z[TPW];
 #pragma unroll
-    for (int ti = 0; ti < TPW; ++ti) {
-        const int t = tw + ti;
-        if (t >= sg.count) break;
-        const long long row = sg.start + t;
+        for (int ti = 0; ti < TPW; ++ti) { acc[ti] = 0.f; z[ti] = 0.f; }
+        const float* kvh = st + (h * D) * (D + 1);
 #pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int h = (32 * j) / D + hs;
-            const float qq = q[ti][j];  // channel h*D + v: this lane's "v" plays the role of d
-            float z = qq * st[(h * D + v) * (D + 1) + D];
+        for (int d4 = 0; d4 < D / 4; ++d4) {
+            float kv[4], ks[4];
 #pragma unroll
-            for (int o = D / 2; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
-            float acc = 0.f;
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const float qd = __shfl_sync(0xffffffffu, qq, hs * D + d);
-                acc = fmaf(qd, st[(h * D + d) * (D + 1) + v], acc);
+            for (int i = 0; i < 4; ++i) {
+                kv[i] = kvh[(4 * d4 + i) * (D + 1) + v];
+                ks[i] = kvh[(4 * d4 + i) * (D + 1) + D];
             }
-            const float r = acc * (1.f / (z + 1e-6f)) * len;
-            __half hh, ll;
-            split_f16(r, hh, ll);
-            out_hi[row * ldo + h * D + v] = hh;
-            out_lo[row * ldo + h * D + v] = ll;
+#pragma unroll
+            for (int ti = 0; ti < TPW; ++ti) {
+                const float4 q4 = *reinterpret_cast<const float4*>(qw + ti * C + h * D + 4 * d4);
+                acc[ti] = fmaf(q4.x, kv[0], acc[ti]); acc[ti] = fmaf(q4.y, kv[1], acc[ti]);
+                acc[ti] = fmaf(q4.z, kv[2], acc[ti]); acc[ti] = fmaf(q4.w, kv[3], acc[ti]);
+                z[ti] = fmaf(q4.x, ks[0], z[ti]); z[ti] = fmaf(q4.y, ks[1], z[ti]);
+                z[ti] = fmaf(q4.z, ks[2], z[ti]); z[ti] = fmaf(q4.w, ks[3], z[ti]);
+            }
+        }
+#pragma unroll
+        for (int ti = 0; ti < TPW; ++ti) {
+            const int t = tw + ti;
+            if (t < sg.count) {
+                const float r = acc[ti] * (1.f / (z[ti] + 1e-6f)) * len;
+                __half hh, ll;
+                split_f16(r, hh, ll);
+                const long long o = static_cast<long long>(sg.start + t) * ldo + h * D + v;
+                out_hi[o] = hh;
+                out_lo[o] = ll;
+            }
         }
     }
 }
