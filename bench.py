@@ -80,6 +80,12 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def cpu_threads():
+    """PyTorch-CPU threads for the reference arm: all host cores up to 32 -- measured on the 128-core B200 host the oracle runs
+    3.4 s/pair at 32 threads, 3.7 s at 64 and 26 s at 128 (oversubscribed intra-op pools), so 32 is the reference's best."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,7 +115,7 @@ def run_reference(args):
         return
     from oracle import loftr_oracle as lo
     from oracle import weights
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(cpu_threads())
     sd = weights.loftr_state_dict(0)
     im0, im1 = util.synth_image(HW, HW, 1000), util.synth_image(HW, HW, 1001)
     data = {"image0": im0, "image1": im1, "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
@@ -191,7 +197,7 @@ def main():
                 data["pair_key"] = ((f"im{i}",), (f"im{j}",))
             matcher(data)
             m = np.concatenate([data["mkpts0_f"].cpu().numpy(), data["mkpts1_f"].cpu().numpy(), data["mconf"].cpu().numpy()[:, None]], -1)
-            d2h += m.nbytes
+            d2h += m.nbytes + 4  # + the match-count readback that sizes the arrays
             res.append(m)
         return res
 
@@ -293,7 +299,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         from oracle import loftr_oracle as lo
-        torch.set_num_threads(os.cpu_count() or 1)
+        torch.set_num_threads(cpu_threads())
         sd = weights.loftr_state_dict(0)
         data = {"image0": host_images[0], "image1": host_images[1], "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
         t0 = time.perf_counter()
@@ -323,6 +329,8 @@ def main():
             "algorithmic_gflop_per_pair": pair_flops(HW, HW) / 1e9, "hp2": hp2,
         }
         print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -14,15 +14,16 @@ static __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __re
                                                         const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                         __half* __restrict__ out_lo) {
     constexpr int IH = kStemTH * 2 + 5, IW = kStemTW * 2 + 5;
-    __shared__ float tile[IH][IW + 1];
+    constexpr int PITCH = 40;  // 16-byte aligned rows: a thread reads 16 consecutive inputs as 4 x float4 for 4 output pixels
+    __shared__ __align__(16) float tile[IH][PITCH];
     const int H2 = H / 2, W2 = W / 2, Wp = W2 + 1;
     const int oy0 = blockIdx.y * kStemTH, ox0 = blockIdx.x * kStemTW;
     const int n = blockIdx.z;
     const float* im = img + static_cast<long long>(n) * H * W;
-    for (int i = threadIdx.x; i < IH * IW; i += 128) {
-        const int ty = i / IW, tx = i - ty * IW;
+    for (int i = threadIdx.x; i < IH * PITCH; i += 128) {
+        const int ty = i / PITCH, tx = i - ty * PITCH;
         const int iy = oy0 * 2 - 3 + ty, ix = ox0 * 2 - 3 + tx;
-        tile[ty][tx] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? im[static_cast<long long>(iy) * W + ix] : 0.f;
+        tile[ty][tx] = (tx < IW && iy >= 0 && iy < H && ix >= 0 && ix < W) ? im[static_cast<long long>(iy) * W + ix] : 0.f;
     }
     const int c = threadIdx.x;
     float wr[49];
@@ -34,20 +35,35 @@ static __global__ void __launch_bounds__(128) stem_conv_kernel(const float* __re
     for (int py = 0; py < kStemTH; ++py) {
         const int oy = oy0 + py;
         if (oy >= H2) break;
-        for (int px = 0; px < kStemTW; ++px) {
-            const int ox = ox0 + px;
-            if (ox >= W2) break;
-            float acc = 0.f;
+#pragma unroll 1
+        for (int pg = 0; pg < kStemTW / 4; ++pg) {  // 4 adjacent output pixels per pass share their input rows
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int ky = 0; ky < 7; ++ky)
+            for (int ky = 0; ky < 7; ++ky) {
+                float in[16];
+                const float4* rp = reinterpret_cast<const float4*>(&tile[py * 2 + ky][pg * 8]);
 #pragma unroll
-                for (int kx = 0; kx < 7; ++kx) acc = fmaf(wr[ky * 7 + kx], tile[py * 2 + ky][px * 2 + kx], acc);
-            acc = fmaxf(acc + b, 0.f);
-            const long long o = (n * img_rows + static_cast<long long>(oy) * Wp + ox) * 128 + c;
-            __half h, l;
-            split_f16(acc, h, l);
-            out_hi[o] = h;
-            out_lo[o] = l;
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = rp[q];
+                    in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+#pragma unroll
+                    for (int kx = 0; kx < 7; ++kx) acc[p] = fmaf(wr[ky * 7 + kx], in[2 * p + kx], acc[p]);
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int ox = ox0 + pg * 4 + p;
+                if (ox < W2) {
+                    const float r = fmaxf(acc[p] + b, 0.f);
+                    const long long o = (n * img_rows + static_cast<long long>(oy) * Wp + ox) * 128 + c;
+                    __half h, l;
+                    split_f16(r, h, l);
+                    out_hi[o] = h;
+                    out_lo[o] = l;
+                }
+            }
         }
     }
 }
@@ -148,18 +164,27 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     for (int v = 0; v < D; ++v) o[v] = acc[v];
     o[D] = ksum;
 }
-// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic).  grid (ceil(SZ/256), segments).
+// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic).  grid (ceil(SZ/64), segments), 64 threads.
+constexpr int kKvFinalThreads = 64;
 template <int D>
-static __global__ void __launch_bounds__(256) kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs, int max_chunks,
-                                                              float* __restrict__ state, int tok_per_cta) {
+static __global__ void __launch_bounds__(kKvFinalThreads) kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs,
+                                                                          int max_chunks, float* __restrict__ state, int tok_per_cta) {
     constexpr int SZ = 8 * D * (D + 1);
     const Seg sg = segs[blockIdx.y];
     const int nch = (sg.valid + tok_per_cta - 1) / tok_per_cta;
-    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int i = blockIdx.x * kKvFinalThreads + threadIdx.x;
     if (i >= SZ) return;
     const float* p = part + static_cast<long long>(blockIdx.y) * max_chunks * SZ + i;
     float s = 0.f;
-    for (int c = 0; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
+    int c = 0;
+    for (; c + 8 <= nch; c += 8) {
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = p[static_cast<long long>(c + q) * SZ];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += v[q];
+    }
+    for (; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
     state[static_cast<long long>(sg.state) * SZ + i] = s;
 }
 // grid (token blocks of 32, segments); block 256 = 8 warps x 4 tokens.  lane + 32 j -> output channel (head, v).
