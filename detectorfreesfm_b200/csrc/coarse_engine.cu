@@ -307,7 +307,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
           kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
                                                                       kKvTokPerCta); }
         { LaunchScope ls("kv", st);
-          kv_final_kernel<32><<<dim3((256 * 33 + kKvFinalThreads - 1) / kKvFinalThreads, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
+          kv_final_kernel<32><<<dim3((256 * 33 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
                                                                                    tok_.kv_state, kKvTokPerCta); }
         { LaunchScope ls("attn", st);
           attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<32>(), st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,

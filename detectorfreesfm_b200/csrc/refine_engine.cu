@@ -171,7 +171,7 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             { LaunchScope ls("kv", st);
               kv_partial_kernel<16><<<dim3(chunks, n_segs), 128, 0, st>>>(qkv_.p + 128, qkv_.p + 256, 384, segs_self, chunks, kvpart_.p, kRefineKvTok); }
             { LaunchScope ls("kv", st);
-              kv_final_kernel<16><<<dim3((8 * 16 * 17 + kKvFinalThreads - 1) / kKvFinalThreads, n_segs), kKvFinalThreads, 0, st>>>(kvpart_.p, segs_self, chunks, kvstate_.p, kRefineKvTok); }
+              kv_final_kernel<16><<<dim3((8 * 16 * 17 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(kvpart_.p, segs_self, chunks, kvstate_.p, kRefineKvTok); }
         }
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.

@@ -164,28 +164,32 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     for (int v = 0; v < D; ++v) o[v] = acc[v];
     o[D] = ksum;
 }
-// state[seg.state][8*D*(D+1)] = sum over chunks (fixed order: deterministic).  grid (ceil(SZ/64), segments), 64 threads.
-constexpr int kKvFinalThreads = 64;
+// state[seg.state][8*D*(D+1)] = sum over chunks in a fixed order (deterministic).  grid (ceil(SZ/64), segments); block
+// (64 outputs x 4 chunk groups): each group sums every 4th chunk, the 4 partial sums are combined through shared memory.
+constexpr int kKvFinalThreads = 256;
 template <int D>
 static __global__ void __launch_bounds__(kKvFinalThreads) kv_final_kernel(const float* __restrict__ part, const Seg* __restrict__ segs,
                                                                           int max_chunks, float* __restrict__ state, int tok_per_cta) {
     constexpr int SZ = 8 * D * (D + 1);
+    __shared__ float red[4][64];
     const Seg sg = segs[blockIdx.y];
     const int nch = (sg.valid + tok_per_cta - 1) / tok_per_cta;
-    const int i = blockIdx.x * kKvFinalThreads + threadIdx.x;
-    if (i >= SZ) return;
-    const float* p = part + static_cast<long long>(blockIdx.y) * max_chunks * SZ + i;
+    const int li = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + li;
     float s = 0.f;
-    int c = 0;
-    for (; c + 8 <= nch; c += 8) {
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = p[static_cast<long long>(c + q) * SZ];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) s += v[q];
+    if (i < SZ) {
+        const float* p = part + static_cast<long long>(blockIdx.y) * max_chunks * SZ + i;
+        int c = grp;
+        for (; c + 12 < nch; c += 16) {
+            const float v0 = p[static_cast<long long>(c) * SZ], v1 = p[static_cast<long long>(c + 4) * SZ];
+            const float v2 = p[static_cast<long long>(c + 8) * SZ], v3 = p[static_cast<long long>(c + 12) * SZ];
+            s += v0; s += v1; s += v2; s += v3;
+        }
+        for (; c < nch; c += 4) s += p[static_cast<long long>(c) * SZ];
     }
-    for (; c < nch; ++c) s += p[static_cast<long long>(c) * SZ];
-    state[static_cast<long long>(sg.state) * SZ + i] = s;
+    red[grp][li] = s;
+    __syncthreads();
+    if (grp == 0 && i < SZ) state[static_cast<long long>(sg.state) * SZ + i] = (red[0][li] + red[1][li]) + (red[2][li] + red[3][li]);
 }
 // grid (token blocks of 32, segments); block 256 = 8 warps x 4 tokens.  lane + 32 j -> output channel (head, v).
 // The warp's 4 query rows are staged in shared memory (coalesced float4 loads issued up front) and read back as broadcast
