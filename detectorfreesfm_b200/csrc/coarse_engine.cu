@@ -50,7 +50,7 @@ struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per si
     float* kv_state = nullptr;
     Seg* seg_dev = nullptr;
     float2* part = nullptr;
-    float2* stat[2] = {nullptr, nullptr};
+    float* stat[2] = {nullptr, nullptr};  // log2-sum-exp2 per row / column
     unsigned long long* best[2] = {nullptr, nullptr};
 };
 
@@ -252,7 +252,7 @@ void CoarseEngine::ensure_tok(int n) {
         tok_.m1[s] = hl_alloc(cap, 256);
         tok_.hid[s] = hl_alloc(cap, 512);
         DFSFM_CUDA(cudaMalloc(&tok_.qkv[s], static_cast<size_t>(cap) * 768 * sizeof(float)));
-        DFSFM_CUDA(cudaMalloc(&tok_.stat[s], static_cast<size_t>(cap) * sizeof(float2)));
+        DFSFM_CUDA(cudaMalloc(&tok_.stat[s], static_cast<size_t>(cap) * sizeof(float)));
         DFSFM_CUDA(cudaMalloc(&tok_.best[s], static_cast<size_t>(cap) * sizeof(unsigned long long)));
     }
     tok_.kv_chunks = (cap + kKvTokPerCta - 1) / kKvTokPerCta;
@@ -260,7 +260,7 @@ void CoarseEngine::ensure_tok(int n) {
     DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(2) * tok_.kv_chunks * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(2) * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 8 * sizeof(Seg)));
-    const int tiles = (cap + 255) / 256;
+    const int tiles = 2 * ((cap + 255) / 256);  // engine 2 writes one partial per half tile
     DFSFM_CUDA(cudaMalloc(&tok_.part, static_cast<size_t>(tiles) * cap * sizeof(float2)));
 }
 
@@ -409,7 +409,7 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         c.M = n[side];
         e.M = n[side]; e.N = n[o]; e.mode = SIM_STATS; e.part = tok_.part;
         launch_gemm_counted<256, true, SimEpi>(maps, c, e, n[o], st, "sim");
-        const int tiles = (n[o] + 255) / 256;
+        const int tiles = ((n[o] + 255) / 256) * (engine_version() == 2 ? 2 : 1);
         { LaunchScope ls("stats_merge", st);
           stats_merge_kernel<<<(n[side] + 255) / 256, 256, 0, st>>>(tok_.part, tiles, n[side], tok_.stat[side]); }
     }
@@ -421,7 +421,7 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         maps.b = make_tmap(tok_.x[1].hi, 256, S, tok_.x[1].plane_elems(), bbox(256));
         c.M = L;
         e.M = L; e.N = S; e.mode = SIM_CONF;
-        e.row_stat = tok_.stat[0]; e.col_stat = tok_.stat[1]; e.thr = thr;
+        e.row_lse = tok_.stat[0]; e.col_lse = tok_.stat[1]; e.thr = thr;
         e.row_best = tok_.best[0]; e.col_best = tok_.best[1]; e.conf_out = conf_out;
         launch_gemm_counted<256, true, SimEpi>(maps, c, e, S, st, "sim");
     }

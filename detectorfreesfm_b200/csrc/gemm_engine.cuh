@@ -22,7 +22,9 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kMaxTaps = 26;
 constexpr int kMaxAMaps = 5;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;   // engine 1: 2 role warps + 4 epilogue warps
+constexpr int kGemm2EpiWarps = 8;  // engine 2: two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kGemm2Threads = 64 + 32 * kGemm2EpiWarps;
 
 struct TmapPack {
     CUtensorMap a[kMaxAMaps];  // activation planes: dims {C, rows, 2 (hi/lo)}, box {64, 128, 1}
@@ -154,7 +156,8 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
         const int quad = warp & 3;  // TMEM lane quadrant this warp may read
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0);
+        Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0, 0, BN,
+                                             static_cast<int>(blockIdx.y));
         tc_fence_before();
     }
     __syncthreads();
@@ -193,7 +196,7 @@ struct Gemm2Cfg {
 };
 
 template <int BN, bool kSplit, class Epi>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
                 const int n_tiles) {
     using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr>;
@@ -220,7 +223,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full_bar[a], 1);
-            mbar_init(&tmem_empty_bar[a], 8);  // 4 epilogue warps x 2 CTAs arrive on the leader's barrier
+            mbar_init(&tmem_empty_bar[a], 2 * kGemm2EpiWarps);  // every epilogue warp of both CTAs arrives on the leader's barrier
         }
         fence_mbar_init();
     }
@@ -299,7 +302,10 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
         }
         __syncwarp();
     } else {
-        const int quad = warp & 3;
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+        const int half = (warp - 2) >> 2;     // which half of the tile's columns this warp handles
+        constexpr int kHalfCols = ((BN / 2 + 31) / 32) * 32;
+        const int cb = half * kHalfCols, ce = half == 0 ? kHalfCols : BN;
         int a = 0;
         uint32_t aphase = 0;
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -308,7 +314,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             mbar_wait(&tmem_full_bar[a], aphase);
             tc_fence_after();
             Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
-                                                 nt * BN);
+                                                 nt * BN, cb, ce, nt * 2 + half);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
@@ -324,6 +330,11 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
 }
 
 // ------------------------------------------------------------------------------------------------ epilogues
+__device__ __forceinline__ float fast_ex2(float x) {  // 2^x, MUFU.EX2 (2 ulp), flushes denormal results to zero
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // 32 accumulator columns of this thread's row: main (+ correction accumulator, added with round-to-nearest).
 template <int kCorr>
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float* v) {
@@ -378,7 +389,7 @@ struct ConvEpi {
     using Params = ConvEpiParams;
     static constexpr bool kSeparateCorr = true;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
         const int row = row0 + lane;
         bool valid = row < p.M;
         int n_img = 0, y = 0, x = 0;
@@ -406,7 +417,7 @@ struct ConvEpi {
             orow = static_cast<long long>(n_img) * p.wh * p.ww + (y - p.wy0) * p.ww + (x - p.wx0);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
             float v[32];
             load_acc32<kCorr>(tmem_warp + c0, v);  // warp-collective: every lane executes it
             const int nb = n0 + c0;
@@ -510,7 +521,7 @@ struct LinEpi {
     using Params = LinEpiParams;
     static constexpr bool kSeparateCorr = false;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         float mean = 0.f, rstd = 0.f;
@@ -531,7 +542,7 @@ struct LinEpi {
             rstd = rsqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
         }
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = cb; c0 < ce; c0 += 32) {
             float v[32];
             load_acc32<kCorr>(tmem_warp + c0, v);
             const int nb = n0 + c0;
@@ -539,7 +550,7 @@ struct LinEpi {
             if (p.mode == LIN_F32_ELU) {
                 if (nb < p.elu_cols) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : expf(v[j]);  // elu(x) + 1 == exp(x) for x <= 0
+                    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] + 1.f : fast_ex2(v[j] * 1.4426950408889634f);  // elu(x) + 1 == exp(x), x <= 0
                 }
             } else if (p.mode == LIN_RELU_HL) {
 #pragma unroll
@@ -588,8 +599,8 @@ struct LinEpi {
 
 // ------------------------------------------------------------------- dual-softmax similarity epilogues
 // t[i,j] = acc[i,j] * c2 with c2 = log2(e) / (d_model * temperature): the similarity in the log2 domain, so that every
-// exponential is one ex2.  SIM_STATS: per-row (max, sum 2^(t-max)) over this CTA's BN columns -> part[blockIdx.y][row].
-// SIM_CONF: conf = softmax_row * softmax_col = 2^(2t - rmax - cmax) / (rsum * csum) from finished row / column
+// exponential is one ex2.  SIM_STATS: per-row (max, sum 2^(t-max)) over this warp's columns -> part[part_idx][row].
+// SIM_CONF: conf = softmax_row * softmax_col = 2^(2t - lse_row - lse_col) with lse = max + log2(sum) from the merged
 // statistics; every entry above thr competes for its row's and its column's best (64-bit atomicMax on (conf bits, ~index)).
 enum SimMode : int { SIM_STATS = 0, SIM_CONF = 1 };
 
@@ -597,9 +608,9 @@ struct SimEpiParams {
     int M, N;       // rows (tokens of A), columns (tokens of B)
     int mode;
     float c2;       // log2(e) / (d_model * temperature)
-    float2* part;   // SIM_STATS: [gridDim.y][M] (max, sum) in the log2 domain
-    const float2* row_stat;  // SIM_CONF: [M] (max, 1/sum)
-    const float2* col_stat;  // SIM_CONF: [N]
+    float2* part;   // SIM_STATS: [partial tiles][M] (max, sum) in the log2 domain
+    const float* row_lse;  // SIM_CONF: [M] log2-sum-exp2 of the row
+    const float* col_lse;  // SIM_CONF: [N]
     float thr;
     unsigned long long* row_best;  // [M]
     unsigned long long* col_best;  // [N]
@@ -614,51 +625,60 @@ struct SimEpi {
     using Params = SimEpiParams;
     static constexpr bool kSeparateCorr = false;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         if (p.mode == SIM_STATS) {
             float m = -INFINITY, s = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cb; c0 < ce; c0 += 32) {
                 float v[32];
                 load_acc32<kCorr>(tmem_warp + c0, v);
                 const int nb = n0 + c0;
                 if (nb >= p.N) continue;
-                float cm = -INFINITY;
                 if (nb + 32 <= p.N) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] *= p.c2; cm = fmaxf(cm, v[j]); }
+                    for (int j = 0; j < 32; ++j) v[j] *= p.c2;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) { v[j] = (nb + j < p.N) ? v[j] * p.c2 : -INFINITY; cm = fmaxf(cm, v[j]); }
+                    for (int j = 0; j < 32; ++j) v[j] = (nb + j < p.N) ? v[j] * p.c2 : -INFINITY;
                 }
-                if (cm > m) { s *= exp2f(m - cm); m = cm; }
+                float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) s += exp2f(v[j] - m);
+                for (int j = 8; j < 32; j += 4) {
+                    m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
+                }
+                const float cm = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                if (cm > m) { s *= fast_ex2(m - cm); m = cm; }
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    s0 += fast_ex2(v[j] - m); s1 += fast_ex2(v[j + 1] - m); s2 += fast_ex2(v[j + 2] - m); s3 += fast_ex2(v[j + 3] - m);
+                }
+                s += (s0 + s1) + (s2 + s3);
             }
-            if (valid) p.part[static_cast<long long>(n0 / BN) * p.M + row] = make_float2(m, s);
+            if (valid) p.part[static_cast<long long>(part_idx) * p.M + row] = make_float2(m, s);
         } else {
-            const float2 rs = valid ? p.row_stat[row] : make_float2(0.f, 1.f);  // (max, 1/sum)
+            const float a_row = valid ? p.row_lse[row] : 0.f;
+            const float c22 = 2.f * p.c2;
             float best = -1.f;
             int best_j = 0;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = cb; c0 < ce; c0 += 32) {
                 float v[32];
                 load_acc32<kCorr>(tmem_warp + c0, v);
                 const int nb = n0 + c0;
-                if (!valid || nb >= p.N) continue;
+                if (nb >= p.N) continue;
+                // lane j holds the column term of column nb + j; +inf for columns past N makes their confidence 0
+                const float b_col = (nb + lane < p.N) ? __ldg(p.col_lse + nb + lane) : INFINITY;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    if (nb + j < p.N) {
-                        const float t = v[j] * p.c2;
-                        const float2 cs = __ldg(p.col_stat + nb + j);
-                        const float conf = exp2f((t - rs.x) + (t - cs.x)) * (rs.y * cs.y);
-                        if (p.conf_out) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
-                        if (conf > p.thr) {
-                            atomicMax(p.col_best + nb + j, pack_best(conf, row));
-                            if (conf > best) { best = conf; best_j = nb + j; }
-                        }
+                    const float bj = __shfl_sync(0xffffffffu, b_col, j);
+                    const float conf = fast_ex2(fmaf(v[j], c22, -a_row) - bj);
+                    if (p.conf_out && valid && nb + j < p.N) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
+                    if (conf > p.thr && valid) {
+                        atomicMax(p.col_best + nb + j, pack_best(conf, row));
+                        if (conf > best) { best = conf; best_j = nb + j; }
                     }
                 }
             }

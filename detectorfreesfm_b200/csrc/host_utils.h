@@ -126,7 +126,7 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
     const int tiles = m_pairs * n_tiles;
     const int max_clusters = sm_count() / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    kern<<<dim3(2 * clusters), kGemmThreads, Cfg::kSmemBytes, st>>>(maps, core, ep, tiles, n_tiles);
+    kern<<<dim3(2 * clusters), kGemm2Threads, Cfg::kSmemBytes, st>>>(maps, core, ep, tiles, n_tiles);
     DFSFM_CUDA(cudaGetLastError());
 }
 

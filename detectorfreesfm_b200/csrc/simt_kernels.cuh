@@ -268,8 +268,8 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
 }
 
 // --------------------------------------------------------------------------------------------------------
-// merge per-column-tile softmax partials (log2 domain): stat[i] = (max, sum 2^(. - max))
-static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T, int M, float2* __restrict__ stat) {
+// merge per-column-tile softmax partials (log2 domain) into lse[i] = max + log2(sum 2^(. - max))
+static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T, int M, float* __restrict__ lse) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M) return;
     float m = -INFINITY;
@@ -279,7 +279,7 @@ static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T
         const float2 p = part[static_cast<long long>(t) * M + i];
         s += p.y * exp2f(p.x - m);
     }
-    stat[i] = make_float2(m, 1.f / s);  // (max, 1 / sum): the confidence pass multiplies
+    lse[i] = m + log2f(s);
 }
 
 // Mutual-nearest-neighbour selection + ordered compaction (CoarseMatching.get_coarse_match,
