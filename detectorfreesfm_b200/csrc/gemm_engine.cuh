@@ -335,6 +335,11 @@ __device__ __forceinline__ float fast_ex2(float x) {  // 2^x, MUFU.EX2 (2 ulp), 
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float ex2_denorm(float x) {  // 2^x keeping subnormal results (thr = 0 must see every conf > 0)
+    float y;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 // 32 accumulator columns of this thread's row: main (+ correction accumulator, added with round-to-nearest).
 template <int kCorr>
 __device__ __forceinline__ void load_acc32(uint32_t taddr, float* v) {
@@ -674,7 +679,7 @@ struct SimEpi {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float bj = __shfl_sync(0xffffffffu, b_col, j);
-                    const float conf = fast_ex2(fmaf(v[j], c22, -a_row) - bj);
+                    const float conf = ex2_denorm(fmaf(v[j], c22, -a_row) - bj);
                     if (p.conf_out && valid && nb + j < p.N) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
                     if (conf > p.thr && valid) {
                         atomicMax(p.col_best + nb + j, pack_best(conf, row));
