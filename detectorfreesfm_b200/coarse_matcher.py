@@ -22,8 +22,12 @@ class B200LoFTR(torch.nn.Module):
         mc = config["match_coarse"]
         if mc["match_type"] != "dual_softmax":
             raise NotImplementedError("only match_type='dual_softmax' is built (the shipped loftr_ds configs)")
-        if config["fine"]["enable"]:
-            raise NotImplementedError("LoFTR fine stage (match type 'coarse_fine') is not built yet: SURVEY.md row a11")
+        self.fine = bool(config["fine"]["enable"])
+        if self.fine:
+            fcfg = config["fine"]
+            if (fcfg["d_model"] != 128 or fcfg["nhead"] != 8 or list(fcfg["layer_names"]) != ["self", "cross"] or config["fine_window_size"] != 5
+                    or not config["fine_concat_coarse_feat"] or tuple(config["resolution"]) != (8, 2)):
+                raise NotImplementedError("fine stage is specialised for the outdoor_ds LoFTR (window 5, d_model 128, ['self','cross'])")
         c = config["coarse"]
         if c["d_model"] != 256 or c["nhead"] != 8 or list(c["layer_names"]) != ["self", "cross"] * 4 or c["attention"] != "linear":
             raise NotImplementedError("engine is specialised for the outdoor_ds LoFTR (d_model 256, 8 heads, 8 layers, linear)")
@@ -62,7 +66,7 @@ class B200LoFTR(torch.nn.Module):
 
     def load_state_dict(self, state_dict, strict=True):
         """Accepts the reference checkpoint layout (``matcher.`` prefix stripped like loftr.py:83-87)."""
-        self._packed = pack_loftr(state_dict)
+        self._packed = pack_loftr(state_dict, fine=self.fine)
         if self._h:
             self._upload()
         self._cache.clear()
@@ -103,13 +107,32 @@ class B200LoFTR(torch.nn.Module):
         image = image.contiguous()
         h, w = H // 8, W // 8
         tokens = torch.empty(h * w, 256, device=self._device, dtype=torch.float32)
-        _lib.check(self._lib.dfsfm_coarse_features(self._h, _lib.ptr(image), H, W, _lib.ptr(self._pe_tokens(h, w)), _lib.ptr(tokens),
-                                                   _lib.stream_ptr()))
+        if self.fine:
+            feat_f = torch.empty((H // 2) * (W // 2), 128, device=self._device, dtype=torch.float32)
+            _lib.check(self._lib.dfsfm_coarse_features_fine(self._h, _lib.ptr(image), H, W, _lib.ptr(self._pe_tokens(h, w)), _lib.ptr(tokens),
+                                                            _lib.ptr(feat_f), _lib.stream_ptr()))
+            out = (tokens, feat_f)
+        else:
+            _lib.check(self._lib.dfsfm_coarse_features(self._h, _lib.ptr(image), H, W, _lib.ptr(self._pe_tokens(h, w)), _lib.ptr(tokens),
+                                                       _lib.stream_ptr()))
+            out = tokens
         if key is not None:
-            self._cache[key] = tokens
+            self._cache[key] = out
             while len(self._cache) > self._cache_size:
                 self._cache.popitem(last=False)
-        return tokens
+        return out
+
+    def fine_match(self, feat_f0, hw0_f, feat_f1, hw1_f, feat_c0, hw0_c, feat_c1, hw1_c, i_ids, j_ids):
+        """FinePreprocess + loftr_fine + FineMatching -> (coords_normed * (W // 2) [M,2], std [M])."""
+        M = int(i_ids.shape[0])
+        coords = torch.zeros(M, 2, device=self._device, dtype=torch.float32)
+        std = torch.zeros(M, device=self._device, dtype=torch.float32)
+        if M > 0:
+            i32, j32 = i_ids.to(torch.int32).contiguous(), j_ids.to(torch.int32).contiguous()
+            _lib.check(self._lib.dfsfm_coarse_fine_match(self._h, _lib.ptr(feat_f0), hw0_f[0], hw0_f[1], _lib.ptr(feat_f1), hw1_f[0], hw1_f[1],
+                                                         _lib.ptr(feat_c0), hw0_c[1], _lib.ptr(feat_c1), hw1_c[1], _lib.ptr(i32), _lib.ptr(j32), M,
+                                                         _lib.ptr(coords), _lib.ptr(std), _lib.stream_ptr()))
+        return coords, std
 
     def transform(self, feat0, feat1):
         """LocalFeatureTransformer (8 layers) in place on [L,256], [S,256] fp32 tokens."""
@@ -152,6 +175,8 @@ class B200LoFTR(torch.nn.Module):
             k1 = names[1][0] if isinstance(names[1], (list, tuple)) else names[1]
         f0 = self.extract_features(im0, k0)
         f1 = self.extract_features(im1, k1)
+        if self.fine:
+            (f0, ff0), (f1, ff1) = f0, f1
         hw0_c = (im0.shape[2] // 8, im0.shape[3] // 8)
         hw1_c = (im1.shape[2] // 8, im1.shape[3] // 8)
         data.update({"hw0_c": torch.Size(hw0_c), "hw1_c": torch.Size(hw1_c)})
@@ -173,5 +198,16 @@ class B200LoFTR(torch.nn.Module):
             "b_ids": b_ids, "i_ids": i_ids, "j_ids": j_ids, "gt_mask": mconf == 0,
             "m_bids": b_ids[keep], "mkpts0_c": mkpts0_c[keep], "mkpts1_c": mkpts1_c[keep], "mconf": mconf[keep],
         })
-        data.update({"mkpts0_f": data["mkpts0_c"], "mkpts1_f": data["mkpts1_c"]})
+        if not self.fine:
+            data.update({"mkpts0_f": data["mkpts0_c"], "mkpts1_f": data["mkpts1_c"]})
+            return None
+        # fine-level refinement (loftr.py:75-81, utils/fine_matching.py:63-74)
+        hw0_f = (im0.shape[2] // 2, im0.shape[3] // 2)
+        hw1_f = (im1.shape[2] // 2, im1.shape[3] // 2)
+        data.update({"hw0_f": torch.Size(hw0_f), "hw1_f": torch.Size(hw1_f), "W": 5})
+        coords2, std = self.fine_match(ff0, hw0_f, ff1, hw1_f, f0, hw0_c, f1, hw1_c, i_ids, j_ids)
+        data["expec_f"] = torch.cat([coords2 / 2, std[:, None]], -1)
+        scale_f = data["hw0_i"][0] / hw0_f[0]
+        scale1_f = scale_f * data["scale1"][b_ids][:, [1, 0]] if "scale0" in data else scale_f
+        data.update({"mkpts0_f": data["mkpts0_c"], "mkpts1_f": data["mkpts1_c"] + (coords2 * scale1_f)[:len(data["mconf"])]})
         return None

@@ -6,6 +6,8 @@
 
 #include "../../include/dfsfm_b200.h"
 #include "engine_common.h"
+#include "fine_kernels.cuh"
+#include "refine_kernels.cuh"
 
 namespace dfsfm {
 
@@ -38,6 +40,20 @@ struct FeatWs {  // backbone workspace for one image geometry
     HL a2, b2, c2;
     ParityBuf p1, p2;
     HL a4, b4, a8, b8, c8;
+    // fine FPN branch (allocated on first use)
+    bool fine = false;
+    HL x3o, t4a, t4b, x2o, t2a, t2b;
+    float* f4 = nullptr;
+    float* f2 = nullptr;
+};
+
+struct FineWs {  // fine-stage workspace for up to `cap` coarse matches
+    int cap = 0;
+    HL win, x, msg, m1, hid, cin, cwin;
+    float *xf = nullptr, *qkv = nullptr, *u = nullptr, *kvstate = nullptr, *kvpart = nullptr, *d_query = nullptr;
+    Seg* segs = nullptr;
+    TrackRec* tracks = nullptr;
+    ViewRec* views = nullptr;
 };
 
 struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per side
@@ -68,7 +84,9 @@ class CoarseEngine {
     }
     ParamStore params;
 
-    void features(const float* img, int H, int W, const float* pe, float* tokens, cudaStream_t st);
+    void features(const float* img, int H, int W, const float* pe, float* tokens, float* feat_f, cudaStream_t st);
+    void fine_match(const float* ff0, int Hf0, int Wf0, const float* ff1, int Hf1, int Wf1, const float* fc0, int w0c, const float* fc1, int w1c,
+                    const int* i_ids, const int* j_ids, int M, float* coords_out, float* std_out, cudaStream_t st);
     void transformer(float* f0, int L, float* f1, int S, cudaStream_t st);
     void match(const float* f0, int h0c, int w0c, const float* f1, int h1c, int w1c, float thr, int border, float temperature, int* i_ids,
                int* j_ids, float* mconf, int* n_matches, int capacity, float* conf_out, cudaStream_t st);
@@ -77,6 +95,10 @@ class CoarseEngine {
     int device_;
     std::map<std::pair<int, int>, FeatWs> feat_ws_;
     TokWs tok_;
+    FineWs fine_;
+    void ensure_fine(int M);
+    void fine_branch(FeatWs& w, float* feat_f, cudaStream_t st);
+    void layer128(int li, bool self, int x0, int xn, int s0, int sn, const Seg* kv_segs, int n_kv, const Seg* apply_segs, int n_apply, cudaStream_t st);
 
     FeatWs& get_feat_ws(int H, int W);
     void ensure_tok(int n);
@@ -126,6 +148,10 @@ void CoarseEngine::free_feat(FeatWs& w) {
     hl_free(w.a2); hl_free(w.b2); hl_free(w.c2); hl_free(w.a4); hl_free(w.b4); hl_free(w.a8); hl_free(w.b8); hl_free(w.c8);
     if (w.p1.base) cudaFree(w.p1.base);
     if (w.p2.base) cudaFree(w.p2.base);
+    if (w.fine) {
+        hl_free(w.x3o); hl_free(w.t4a); hl_free(w.t4b); hl_free(w.x2o); hl_free(w.t2a); hl_free(w.t2b);
+        cudaFree(w.f4); cudaFree(w.f2);
+    }
 }
 
 template <int BN>
@@ -161,7 +187,7 @@ static ConvEpiParams epi_parity(const Geom& g, int N, const ParityBuf& out, bool
     return e;
 }
 
-void CoarseEngine::features(const float* img, int H, int W, const float* pe, float* tokens, cudaStream_t st) {
+void CoarseEngine::features(const float* img, int H, int W, const float* pe, float* tokens, float* feat_f, cudaStream_t st) {
     DFSFM_CHECK(H % 8 == 0 && W % 8 == 0 && H >= 16 && W >= 16, "image size must be a multiple of 8 (CoarseMatchingDataset df=8)");
     FeatWs& w = get_feat_ws(H, W);
     // conv1 + bn1 + relu (resnet_fpn.py:102)
@@ -218,8 +244,78 @@ void CoarseEngine::features(const float* img, int H, int W, const float* pe, flo
         e.out_mode = OUT_DENSE;
         e.out_f32 = tokens;
         e.out_f32_ld = 256;
+        if (feat_f) {
+            if (!w.fine) {
+                w.x3o = hl_alloc(w.g8.rows, 256);
+                w.t4a = hl_alloc(w.g4.rows, 256); w.t4b = hl_alloc(w.g4.rows, 256); w.x2o = hl_alloc(w.g4.rows, 208);
+                w.t2a = hl_alloc(w.g2.rows, 208); w.t2b = hl_alloc(w.g2.rows, 208);
+                DFSFM_CUDA(cudaMalloc(&w.f4, static_cast<size_t>(w.g4.rows) * 256 * sizeof(float)));
+                DFSFM_CUDA(cudaMalloc(&w.f2, static_cast<size_t>(w.g2.rows) * 208 * sizeof(float)));
+                w.fine = true;
+            }
+            // tokens get x3_out + PE; the raw x3_out planes (same flat geometry, no PE) feed the FPN top-down path.
+            // OUT_DENSE and OUT_FLAT differ only in the row mapping, so the planes come from a second epilogue pass below.
+        }
         const HL in[1] = {w.c8};
         conv<256>(in, 1, c, "out3", e, st);
+        if (feat_f) {
+            ConvEpiParams e2 = epi_flat(w.g8, 256, w.x3o, false, nullptr);
+            conv<256>(in, 1, c, "out3", e2, st);
+            fine_branch(w, feat_f, st);
+        }
+    }
+}
+
+// FPN top-down path to the 1/2-resolution fine feature map (resnet_fpn.py:110-118), only for match type 'coarse_fine'.
+void CoarseEngine::fine_branch(FeatWs& w, float* feat_f, cudaStream_t st) {
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    auto up_add = [&](const HL& low, const Geom& gl, int C, const float* lateral, const HL& out) {
+        const long long total = static_cast<long long>(2 * gl.H) * (2 * gl.W) * (C / 8);
+        LaunchScope ls("upsample", st);
+        upsample2x_add_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(low.hi, low.lo(), gl.H, gl.W, C, lateral, out.hi, out.lo(), total);
+        DFSFM_CUDA(cudaGetLastError());
+    };
+    // x2_out = layer2_outconv(x2) [1x1 on the four parity planes of x2] + up(x3_out)
+    c.M = static_cast<int>(w.g8.rows);
+    set_k(c, 208);
+    conv_taps_s1(c, 1, w.g8.Wp);
+    for (int k = 0; k < 4; ++k) {
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.N = 256; e.g = w.g8.flat(); e.out_mode = OUT_UNPARITY; e.upy = k >> 1; e.upx = k & 1; e.ohp = w.g4.Hp; e.owp = w.g4.Wp;
+        e.out_f32 = w.f4; e.out_f32_ld = 256;
+        const HL in[1] = {w.p2.plane(k)};
+        conv<256>(in, 1, c, "fpn.l2o", e, st);
+    }
+    up_add(w.x3o, w.g8, 256, w.f4, w.t4a);
+    c.M = static_cast<int>(w.g4.rows);
+    set_k(c, 256);
+    conv_taps_s1(c, 3, w.g4.Wp);
+    { ConvEpiParams e = epi_flat(w.g4, 256, w.t4b, false, nullptr); e.relu = 2; const HL in[1] = {w.t4a}; conv<256>(in, 1, c, "fpn.l2o2a", e, st); }
+    { ConvEpiParams e = epi_flat(w.g4, 208, w.x2o, false, nullptr); const HL in[1] = {w.t4b}; conv<208>(in, 1, c, "fpn.l2o2b", e, st); }
+    // x1_out = layer1_outconv(x1) [1x1 on the parity planes of x1] + up(x2_out)
+    set_k(c, 128);
+    conv_taps_s1(c, 1, w.g4.Wp);
+    for (int k = 0; k < 4; ++k) {
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.N = 208; e.g = w.g4.flat(); e.out_mode = OUT_UNPARITY; e.upy = k >> 1; e.upx = k & 1; e.ohp = w.g2.Hp; e.owp = w.g2.Wp;
+        e.out_f32 = w.f2; e.out_f32_ld = 208;
+        const HL in[1] = {w.p1.plane(k)};
+        conv<208>(in, 1, c, "fpn.l1o", e, st);
+    }
+    up_add(w.x2o, w.g4, 208, w.f2, w.t2a);
+    c.M = static_cast<int>(w.g2.rows);
+    set_k(c, 208);
+    conv_taps_s1(c, 3, w.g2.Wp);
+    { ConvEpiParams e = epi_flat(w.g2, 208, w.t2b, false, nullptr); e.relu = 2; const HL in[1] = {w.t2a}; conv<208>(in, 1, c, "fpn.l1o2a", e, st); }
+    {
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.N = 128; e.g = w.g2.flat(); e.out_mode = OUT_DENSE; e.out_f32 = feat_f; e.out_f32_ld = 128;
+        const HL in[1] = {w.t2b};
+        conv<128>(in, 1, c, "fpn.l1o2b", e, st);
     }
 }
 
@@ -430,6 +526,191 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
     DFSFM_CUDA(cudaGetLastError());
 }
 
+
+// ------------------------------------------------------------------------------------------------ fine stage
+void CoarseEngine::ensure_fine(int M) {
+    FineWs& f = fine_;
+    if (M <= f.cap) return;
+    hl_free(f.win); hl_free(f.x); hl_free(f.msg); hl_free(f.m1); hl_free(f.hid); hl_free(f.cin); hl_free(f.cwin);
+    for (float* q : {f.xf, f.qkv, f.u, f.kvstate, f.kvpart, f.d_query}) if (q) cudaFree(q);
+    if (f.segs) cudaFree(f.segs);
+    if (f.tracks) cudaFree(f.tracks);
+    if (f.views) cudaFree(f.views);
+    const int cap = ((M + 1023) / 1024) * 1024;
+    f.cap = cap;
+    const long long R = 2ll * cap * 25;
+    f.win = hl_alloc(R, 128); f.x = hl_alloc(R, 128); f.msg = hl_alloc(R, 128); f.m1 = hl_alloc(R, 128); f.hid = hl_alloc(R, 256);
+    f.cin = hl_alloc(2ll * cap, 256); f.cwin = hl_alloc(2ll * cap, 128);
+    DFSFM_CUDA(cudaMalloc(&f.xf, static_cast<size_t>(R) * 128 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.qkv, static_cast<size_t>(R) * 384 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.u, static_cast<size_t>(2) * cap * 128 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.kvstate, static_cast<size_t>(2) * cap * 2176 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.kvpart, static_cast<size_t>(2) * cap * 2176 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.d_query, static_cast<size_t>(cap) * 2 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&f.segs, static_cast<size_t>(4) * cap * sizeof(Seg)));
+    DFSFM_CUDA(cudaMalloc(&f.tracks, static_cast<size_t>(cap) * sizeof(TrackRec)));
+    DFSFM_CUDA(cudaMalloc(&f.views, static_cast<size_t>(cap) * sizeof(ViewRec)));
+}
+
+// One LoFTREncoderLayer of loftr_fine (d_model 128, 8 heads) on token rows [x0, x0+xn) of the window-token array; source rows
+// [s0, s0+sn) when not self.  Same structure as layer_call, 128-wide.
+void CoarseEngine::layer128(int li, bool self, int x0, int xn, int s0, int sn, const Seg* kv_segs, int n_kv, const Seg* apply_segs, int n_apply,
+                            cudaStream_t st) {
+    FineWs& f = fine_;
+    const std::string p = "fine.tr." + std::to_string(li);
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    set_k(c, 128);
+    conv_taps_s1(c, 1, 0);
+    LinEpiParams e;
+    auto rows_map = [&](const HL& b, int r0, int n) { return make_tmap(b.hi + static_cast<long long>(r0) * b.C, b.C, n, b.plane_elems(), kBM); };
+    {
+        TmapPack maps;
+        maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128));
+        memset(&e, 0, sizeof(e));
+        e.mode = LIN_F32_ELU;
+        e.out_f32_ld = 384;
+        if (self) {
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.x, x0, xn);
+            c.M = xn; c.b_row0 = 0;
+            e.M = xn; e.N = 384; e.elu_cols = 256; e.out_f32 = f.qkv + static_cast<long long>(x0) * 384; e.out_col0 = 0;
+            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 384, st, "fine_lin");
+        } else {
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.x, x0, xn);
+            c.M = xn; c.b_row0 = 0;
+            e.M = xn; e.N = 128; e.elu_cols = 128; e.out_f32 = f.qkv + static_cast<long long>(x0) * 384; e.out_col0 = 0;
+            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st, "fine_lin");
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.x, s0, sn);
+            c.M = sn; c.b_row0 = 128;
+            e.M = sn; e.N = 256; e.elu_cols = 128; e.out_f32 = f.qkv + static_cast<long long>(s0) * 384; e.out_col0 = 128;
+            launch_gemm_counted<128, true, LinEpi>(maps, c, e, 256, st, "fine_lin");
+        }
+    }
+    { LaunchScope ls("fine_kv", st);
+      kv_partial_kernel<16><<<dim3(1, n_kv), 128, 0, st>>>(f.qkv + 128, f.qkv + 256, 384, kv_segs, 1, f.kvpart, 32); }
+    { LaunchScope ls("fine_kv", st);
+      kv_final_kernel<16><<<dim3((8 * 16 * 17 + 63) / 64, n_kv), kKvFinalThreads, 0, st>>>(f.kvpart, kv_segs, 1, f.kvstate, 32); }
+    { LaunchScope ls("fine_attn", st);
+      attn_apply_kernel<16><<<dim3(1, n_apply), 256, attn_smem_bytes<16>(), st>>>(f.qkv, 384, apply_segs, f.kvstate, f.msg.hi, f.msg.lo(), 128); }
+    DFSFM_CUDA(cudaGetLastError());
+    c.M = xn; c.b_row0 = 0;
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.msg, x0, xn);
+        maps.b = make_tmap(params.mat(p + ".merge"), bbox(128));
+        memset(&e, 0, sizeof(e));
+        e.M = xn; e.N = 128; e.mode = LIN_LN; e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
+        e.out_hi = f.m1.hi + static_cast<long long>(x0) * 128; e.out_lo = f.m1.lo() + static_cast<long long>(x0) * 128; e.out_ld = 128;
+        launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st, "fine_lin");
+    }
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(i == 1 ? f.m1 : f.x, x0, xn);
+        maps.b = make_tmap(params.mat(p + ".mlp0"), bbox(256));
+        GemmCore c2 = c;
+        c2.num_taps = 2; c2.tap_map[0] = 0; c2.tap_map[1] = 1; c2.tap_shift[0] = c2.tap_shift[1] = 0;
+        memset(&e, 0, sizeof(e));
+        e.M = xn; e.N = 256; e.mode = LIN_RELU_HL;
+        e.out_hi = f.hid.hi + static_cast<long long>(x0) * 256; e.out_lo = f.hid.lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
+        launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 256, st, "fine_lin");
+    }
+    {
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.hid, x0, xn);
+        maps.b = make_tmap(params.mat(p + ".mlp2"), bbox(128));
+        GemmCore c3 = c;
+        set_k(c3, 256);
+        memset(&e, 0, sizeof(e));
+        e.M = xn; e.N = 128; e.mode = LIN_LN; e.gamma = params.vec(p + ".ln2.g"); e.beta = params.vec(p + ".ln2.b");
+        e.resid = f.xf + static_cast<long long>(x0) * 128; e.resid_ld = 128;
+        e.out_f32 = f.xf + static_cast<long long>(x0) * 128; e.out_f32_ld = 128;
+        e.out_hi = f.x.hi + static_cast<long long>(x0) * 128; e.out_lo = f.x.lo() + static_cast<long long>(x0) * 128; e.out_ld = 128;
+        launch_gemm_counted<128, true, LinEpi>(maps, c3, e, 128, st, "fine_lin");
+    }
+}
+
+// FinePreprocess.forward + loftr_fine + FineMatching.forward (fine_preprocess.py:29-59, transformer.py:80-101,
+// utils/fine_matching.py:15-61) for M coarse matches.  coords_out [M][2] = coords_normed * (W // 2); std_out [M].
+void CoarseEngine::fine_match(const float* ff0, int Hf0, int Wf0, const float* ff1, int Hf1, int Wf1, const float* fc0, int w0c, const float* fc1,
+                              int w1c, const int* i_ids, const int* j_ids, int M, float* coords_out, float* std_out, cudaStream_t st) {
+    if (M <= 0) return;
+    ensure_fine(M);
+    FineWs& f = fine_;
+    const int stride = Wf0 / w0c;  // hw0_f // hw0_c (fine_preprocess.py:31)
+    const int MW = M * 25, R = 2 * MW;
+    // host tables: attention segments (window = 25 tokens) and the per-match records of the matching kernel
+    std::vector<Seg> segs(static_cast<size_t>(4) * M);
+    std::vector<TrackRec> tracks(M);
+    std::vector<ViewRec> views(M);
+    for (int w = 0; w < 2 * M; ++w) segs[w] = Seg{w * 25, 25, 25, w};
+    for (int m = 0; m < M; ++m) {
+        segs[static_cast<size_t>(2) * M + m] = Seg{m * 25, 25, 25, M + m};        // feat0 windows read the feat1 states
+        segs[static_cast<size_t>(3) * M + m] = Seg{(M + m) * 25, 25, 25, m};      // feat1 windows read the (updated) feat0 states
+        TrackRec& t = tracks[m];
+        t.tok0 = m * 25; t.qtok0 = (M + m) * 25; t.n_views = 1; t.movable = 0; t.qx = t.qy = 0.f; t.sqx = t.sqy = 1.f;
+        views[m] = ViewRec{0.f, 0.f, 1.f, 1.f};
+    }
+    DFSFM_CUDA(cudaMemcpyAsync(f.segs, segs.data(), segs.size() * sizeof(Seg), cudaMemcpyHostToDevice, st));
+    DFSFM_CUDA(cudaMemcpyAsync(f.tracks, tracks.data(), tracks.size() * sizeof(TrackRec), cudaMemcpyHostToDevice, st));
+    DFSFM_CUDA(cudaMemcpyAsync(f.views, views.data(), views.size() * sizeof(ViewRec), cudaMemcpyHostToDevice, st));
+    { LaunchScope ls("fine_gather", st);
+      gather_windows_kernel<<<2 * M, 128, 0, st>>>(ff0, Hf0, Wf0, w0c, ff1, Hf1, Wf1, w1c, stride, i_ids, j_ids, M, f.win.hi, f.win.lo()); }
+    { LaunchScope ls("fine_gather", st);
+      gather_coarse_kernel<<<2 * M, 256, 0, st>>>(fc0, fc1, i_ids, j_ids, M, f.cin.hi, f.cin.lo()); }
+    DFSFM_CUDA(cudaGetLastError());
+    GemmCore c;
+    memset(&c, 0, sizeof(c));
+    conv_taps_s1(c, 1, 0);
+    auto rows_map = [&](const HL& b, int n) { return make_tmap(b.hi, b.C, n, b.plane_elems(), kBM); };
+    {   // c_win = down_proj(cat[feat_c0[i], feat_c1[j]])                      (fine_preprocess.py:50-51)
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.cin, 2 * M);
+        maps.b = make_tmap(params.mat("fine.down.w"), bbox(128));
+        set_k(c, 256);
+        c.M = 2 * M;
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.M = 2 * M; e.N = 128; e.bias = params.vec("fine.down.b"); e.out_mode = OUT_FLAT;
+        e.out_hi = f.cwin.hi; e.out_lo = f.cwin.lo(); e.out_ld = 128;
+        launch_gemm_counted<128, true, ConvEpi>(maps, c, e, 128, st, "fine_lin");
+    }
+    {   // u = merge_feat.weight[:, 128:] . c_win + merge_feat.bias   (the coarse half of the concat, constant over a window)
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.cwin, 2 * M);
+        maps.b = make_tmap(params.mat("fine.merge_c.w"), bbox(128));
+        set_k(c, 128);
+        c.M = 2 * M;
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.M = 2 * M; e.N = 128; e.bias = params.vec("fine.merge.b"); e.out_mode = OUT_FLAT; e.out_f32 = f.u; e.out_f32_ld = 128;
+        launch_gemm_counted<128, true, ConvEpi>(maps, c, e, 128, st, "fine_lin");
+    }
+    {   // tokens = merge_feat.weight[:, :128] . window + u[window]          (fine_preprocess.py:52-56)
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(f.win, R);
+        maps.b = make_tmap(params.mat("fine.merge_f.w"), bbox(128));
+        set_k(c, 128);
+        c.M = R;
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.M = R; e.N = 128; e.g = FlatGeom{25, 1, 25, 1};  // "image" = window, 25 rows: n_img indexes u
+        e.addend = f.u; e.addend_mode = 1; e.out_mode = OUT_FLAT;
+        e.out_f32 = f.xf; e.out_f32_ld = 128; e.out_hi = f.x.hi; e.out_lo = f.x.lo(); e.out_ld = 128;
+        launch_gemm_counted<128, true, ConvEpi>(maps, c, e, 128, st, "fine_lin");
+    }
+    // loftr_fine: ['self', 'cross'] (default.py:44), cross = feat0 first, then feat1 against the updated feat0
+    layer128(0, true, 0, R, 0, R, f.segs, 2 * M, f.segs, 2 * M, st);
+    layer128(1, false, 0, MW, MW, MW, f.segs + M, M, f.segs + 2 * M, M, st);
+    layer128(1, false, MW, MW, 0, MW, f.segs, M, f.segs + 3 * M, M, st);
+    {   // FineMatching: centre token of window 0 against the 25 tokens of window 1, soft-argmax + std
+        const size_t smem = (static_cast<size_t>(1) * 128 + static_cast<size_t>(25) * 129 + static_cast<size_t>(kMaxViews) * 3) * sizeof(float);
+        DFSFM_CUDA(cudaMemsetAsync(coords_out, 0, static_cast<size_t>(M) * 2 * sizeof(float), st));
+        LaunchScope ls("fine_match", st);
+        fine_match_kernel<<<M, kFmThreads, smem, st>>>(f.xf, f.tracks, f.views, 1, 5, 1, f.d_query, coords_out, std_out, M);
+        DFSFM_CUDA(cudaGetLastError());
+    }
+}
+
 }  // namespace dfsfm
 
 // ================================================================================================ C ABI
@@ -451,7 +732,19 @@ int dfsfm_coarse_set_param(dfsfm_coarse_t* h, const char* name, const float* hos
     return dfsfm::guard([&] { h->e->params.set(name, host, rows, cols, kind); });
 }
 int dfsfm_coarse_features(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev, void* stream) {
-    return dfsfm::guard([&] { h->e->features(image_dev, H, W, pe_dev, tokens_out_dev, static_cast<cudaStream_t>(stream)); });
+    return dfsfm::guard([&] { h->e->features(image_dev, H, W, pe_dev, tokens_out_dev, nullptr, static_cast<cudaStream_t>(stream)); });
+}
+int dfsfm_coarse_features_fine(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev,
+                               float* feat_f_out_dev, void* stream) {
+    return dfsfm::guard([&] { h->e->features(image_dev, H, W, pe_dev, tokens_out_dev, feat_f_out_dev, static_cast<cudaStream_t>(stream)); });
+}
+int dfsfm_coarse_fine_match(dfsfm_coarse_t* h, const float* feat_f0_dev, int Hf0, int Wf0, const float* feat_f1_dev, int Hf1, int Wf1,
+                            const float* feat_c0_dev, int w0c, const float* feat_c1_dev, int w1c, const int32_t* i_ids_dev,
+                            const int32_t* j_ids_dev, int M, float* coords_out_dev, float* std_out_dev, void* stream) {
+    return dfsfm::guard([&] {
+        h->e->fine_match(feat_f0_dev, Hf0, Wf0, feat_f1_dev, Hf1, Wf1, feat_c0_dev, w0c, feat_c1_dev, w1c, i_ids_dev, j_ids_dev, M, coords_out_dev,
+                         std_out_dev, static_cast<cudaStream_t>(stream));
+    });
 }
 int dfsfm_coarse_transformer(dfsfm_coarse_t* h, float* feat0_dev, int L, float* feat1_dev, int S, void* stream) {
     return dfsfm::guard([&] { h->e->transformer(feat0_dev, L, feat1_dev, S, static_cast<cudaStream_t>(stream)); });

@@ -368,6 +368,7 @@ enum OutMode : int {
     OUT_DENSE = 2,   // dense token rows n*H*W + y*W + x
     OUT_WINDOW = 3,  // a (wh x ww) window at (y0,x0) re-packed into its own flat-halo geometry (ohp x owp per image)
     OUT_WINDOW_DENSE = 4,  // the window re-packed into dense rows n*wh*ww + y*ww + x
+    OUT_UNPARITY = 5,      // the input geometry is parity plane (upy,upx): pixel (y,x) lands at (2y+upy, 2x+upx) of a flat geometry (ohp x owp)
 };
 
 struct ConvEpiParams {
@@ -378,7 +379,9 @@ struct ConvEpiParams {
     const __half* res_hi;  // optional residual in the input flat geometry
     const __half* res_lo;
     int res_ld;
-    const float* addend;  // optional fp32 addend indexed [y*W + x][N] (position encoding)
+    const float* addend;  // optional fp32 addend [.][N]
+    int addend_mode;      // 0: row (y*W + x), added to the fp32 output only, after activation (position encoding next to raw planes);
+                          // 1: row n_img (one vector per image / window), added before the activation to every output
     int out_mode;
     __half* out_hi;
     __half* out_lo;
@@ -387,7 +390,8 @@ struct ConvEpiParams {
     float* out_f32;          // optional fp32 copy (same row mapping as out_hi)
     int out_f32_ld;
     int wy0, wx0, wh, ww;    // OUT_WINDOW / OUT_WINDOW_DENSE
-    int ohp, owp;            // OUT_WINDOW: rows / pitch of the output geometry
+    int ohp, owp;            // OUT_WINDOW / OUT_UNPARITY: rows / pitch of the output geometry
+    int upy, upx;            // OUT_UNPARITY
 };
 
 struct ConvEpi {
@@ -420,6 +424,8 @@ struct ConvEpi {
         } else if (p.out_mode == OUT_WINDOW_DENSE) {
             valid = valid && y >= p.wy0 && y < p.wy0 + p.wh && x >= p.wx0 && x < p.wx0 + p.ww;
             orow = static_cast<long long>(n_img) * p.wh * p.ww + (y - p.wy0) * p.ww + (x - p.wx0);
+        } else if (p.out_mode == OUT_UNPARITY) {
+            orow = static_cast<long long>(n_img) * p.ohp * p.owp + (2 * y + p.upy) * p.owp + (2 * x + p.upx);
         }
 #pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
@@ -457,8 +463,8 @@ struct ConvEpi {
                     }
                 }
             }
-            if (p.addend) {
-                const float* ad = p.addend + static_cast<long long>(y * p.g.W + x) * p.N + nb;
+            if (p.addend && p.addend_mode == 1) {
+                const float* ad = p.addend + static_cast<long long>(n_img) * p.N + nb;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     if (j < ncnt) {
@@ -467,9 +473,12 @@ struct ConvEpi {
                     }
                 }
             }
-            if (p.relu) {
+            if (p.relu == 1) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (p.relu == 2) {  // LeakyReLU(0.01) of the FPN fine branch (resnet_fpn.py:63,70)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : 0.01f * v[j];
             }
             if (p.out_hi) {
                 __half* oh = p.out_hi + obase + orow * p.out_ld + nb;
@@ -484,6 +493,16 @@ struct ConvEpi {
                         for (int q = 0; q < 8; ++q) split_f16(v[j + q], hh[q], hl[q]);
                         *reinterpret_cast<uint4*>(oh + j) = uh;
                         if (ol) *reinterpret_cast<uint4*>(ol + j) = ul;
+                    }
+                }
+            }
+            if (p.addend && p.addend_mode == 0) {
+                const float* ad = p.addend + static_cast<long long>(y * p.g.W + x) * p.N + nb;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (j < ncnt) {
+                        const float4 a4 = __ldg(reinterpret_cast<const float4*>(ad + j));
+                        v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
                     }
                 }
             }

@@ -258,6 +258,7 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
         DFSFM_CHECK(k >= 1, "every track needs at least one valid query view");
         TrackRec& tr = tracks[t];
         tr.tok0 = p0 * WW;
+        tr.qtok0 = (p0 + 1) * WW;
         tr.n_views = k;
         tr.movable = movable ? (movable[t] != 0) : 1;
         tr.qx = query_pts[t * 2 + 0];

@@ -164,7 +164,8 @@ static __global__ void __launch_bounds__(128) bicubic_merge_kernel(const float* 
 // over the W*W window, expectation (x,y) on the [-1,1] grid, std = sum sqrt(clamp(var, 1e-10)); score[l] = mean over
 // views of std; best l = first arg-min (centre if the reference point is not movable).  CTA per track.
 struct TrackRec {
-    int tok0;      // first token row of the reference patch; query view n starts at tok0 + (n+1)*W*W
+    int tok0;      // first token row of the reference patch
+    int qtok0;     // first token row of query view 0; view n starts at qtok0 + n*W*W
     int n_views;   // valid query views
     int movable;
     float qx, qy;        // query_points (orig px)
@@ -202,7 +203,7 @@ static __global__ void __launch_bounds__(kFmThreads) fine_match_kernel(const flo
     const float step = 2.f / static_cast<float>(W - 1);
     for (int n = 0; n < tr.n_views; ++n) {
         __syncthreads();
-        const float* q = tokens + (static_cast<long long>(tr.tok0) + static_cast<long long>(n + 1) * WW) * C;
+        const float* q = tokens + (static_cast<long long>(tr.qtok0) + static_cast<long long>(n) * WW) * C;
         for (int i = threadIdx.x; i < WW * C; i += kFmThreads) {
             const int r = i / C, c = i - r * C;
             qry[r * (C + 1) + c] = q[i];

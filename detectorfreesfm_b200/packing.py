@@ -38,7 +38,7 @@ def _padvec(v, n):
     return out
 
 
-def pack_loftr(sd):
+def pack_loftr(sd, fine=False):
     """-> dict name -> (tensor fp32 2-D, kind) for dfsfm_coarse_set_param (kind 0 = GEMM operand, 1 = fp32)."""
     sd = {k.replace("matcher.", "", 1) if k.startswith("matcher.") else k: v for k, v in sd.items()}
     out = {}
@@ -74,6 +74,33 @@ def pack_loftr(sd):
             put(f"l{li}.{bi}.c2.b", bias2, 1)
         cin = d
     put("out3.w", conv_matrix(sd["backbone.layer3_outconv.weight"]), 0)
+    if fine:
+        # FPN top-down path (resnet_fpn.py:56-73): 1x1 laterals on the stored (padded) channel counts, 3x3 + BN + LeakyReLU, 3x3
+        put("fpn.l2o.w", conv_matrix(sd["backbone.layer2_outconv.weight"], None, 256, 208), 0)
+        s_, b_ = _fold_bn(sd, "backbone.layer2_outconv2.1")
+        put("fpn.l2o2a.w", conv_matrix(sd["backbone.layer2_outconv2.0.weight"], s_, 256, 256), 0)
+        put("fpn.l2o2a.b", b_, 1)
+        put("fpn.l2o2b.w", conv_matrix(sd["backbone.layer2_outconv2.3.weight"], None, 208, 256), 0)
+        put("fpn.l1o.w", conv_matrix(sd["backbone.layer1_outconv.weight"], None, 208, 128), 0)
+        s_, b_ = _fold_bn(sd, "backbone.layer1_outconv2.1")
+        put("fpn.l1o2a.w", conv_matrix(sd["backbone.layer1_outconv2.0.weight"], s_, 208, 208), 0)
+        put("fpn.l1o2a.b", _padvec(b_, 208), 1)
+        put("fpn.l1o2b.w", conv_matrix(sd["backbone.layer1_outconv2.3.weight"], None, 128, 208), 0)
+        # FinePreprocess (fine_preprocess.py:18-20): merge_feat acts on cat[window (128), down_proj(coarse) (128)]
+        put("fine.down.w", sd["fine_preprocess.down_proj.weight"], 0)
+        put("fine.down.b", sd["fine_preprocess.down_proj.bias"], 1)
+        put("fine.merge_f.w", sd["fine_preprocess.merge_feat.weight"][:, :128], 0)
+        put("fine.merge_c.w", sd["fine_preprocess.merge_feat.weight"][:, 128:], 0)
+        put("fine.merge.b", sd["fine_preprocess.merge_feat.bias"], 1)
+        for i in range(2):
+            p = f"loftr_fine.layers.{i}"
+            put(f"fine.tr.{i}.qkv", torch.cat([sd[p + ".q_proj.weight"], sd[p + ".k_proj.weight"], sd[p + ".v_proj.weight"]], 0), 0)
+            put(f"fine.tr.{i}.merge", sd[p + ".merge.weight"], 0)
+            put(f"fine.tr.{i}.mlp0", sd[p + ".mlp.0.weight"], 0)
+            put(f"fine.tr.{i}.mlp2", sd[p + ".mlp.2.weight"], 0)
+            for n in ("1", "2"):
+                put(f"fine.tr.{i}.ln{n}.g", sd[p + f".norm{n}.weight"], 1)
+                put(f"fine.tr.{i}.ln{n}.b", sd[p + f".norm{n}.bias"], 1)
     for i in range(8):
         p = f"loftr_coarse.layers.{i}"
         put(f"tr.{i}.qkv", torch.cat([sd[p + ".q_proj.weight"], sd[p + ".k_proj.weight"], sd[p + ".v_proj.weight"]], 0), 0)

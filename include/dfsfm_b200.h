@@ -41,6 +41,20 @@ int dfsfm_coarse_set_param(dfsfm_coarse_t* h, const char* name, const float* hos
 int dfsfm_coarse_features(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev,
                           void* stream);
 
+/* Same, plus the FPN top-down path to the 1/2-resolution fine map x1_out (resnet_fpn.py:110-118, match type 'coarse_fine'):
+ * feat_f_out_dev [(H/2)*(W/2)][128] fp32 (NHWC rows). */
+int dfsfm_coarse_features_fine(dfsfm_coarse_t* h, const float* image_dev, int H, int W, const float* pe_dev, float* tokens_out_dev,
+                               float* feat_f_out_dev, void* stream);
+
+/* FinePreprocess.forward + loftr_fine + FineMatching.forward (loftr_module/fine_preprocess.py:29-59, transformer.py:80-101 with
+ * d_model 128 / 2 layers, utils/fine_matching.py:15-61) for the M coarse matches (i_ids, j_ids):
+ * feat_f*: fine maps [Hf*Wf][128]; feat_c*: coarse tokens AFTER the coarse transformer; w*c: coarse grid widths.
+ * coords_out_dev [M][2] = coords_normed * (W // 2) (multiply by scale * scale1 to get the mkpts1_f offset, fine_matching.py:70-72);
+ * std_out_dev [M] (expec_f[:, 2]). */
+int dfsfm_coarse_fine_match(dfsfm_coarse_t* h, const float* feat_f0_dev, int Hf0, int Wf0, const float* feat_f1_dev, int Hf1, int Wf1,
+                            const float* feat_c0_dev, int w0c, const float* feat_c1_dev, int w1c, const int32_t* i_ids_dev,
+                            const int32_t* j_ids_dev, int M, float* coords_out_dev, float* std_out_dev, void* stream);
+
 /* LocalFeatureTransformer.forward (loftr_module/transformer.py:80-101), in place on feat0_dev [L][256], feat1_dev [S][256]. */
 int dfsfm_coarse_transformer(dfsfm_coarse_t* h, float* feat0_dev, int L, float* feat1_dev, int S, void* stream);
 

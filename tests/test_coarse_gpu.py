@@ -85,3 +85,41 @@ def test_end_to_end_pair(sd, temperature, thr):
         assert (data["mconf"].cpu() - ref["mconf"]).abs().max().item() < 1e-3
         assert torch.equal(data["mkpts0_f"].cpu(), ref["mkpts0_f"]) and torch.equal(data["mkpts1_f"].cpu(), ref["mkpts1_f"])
     assert (data["m_bids"] == 0).all()
+
+
+# ------------------------------------------------------------------------------------------- fine stage (row a11)
+@pytest.mark.parametrize("hw", [(96, 128), (64, 80)])
+def test_fine_feature_map(sd, hw):
+    """FPN top-down path: x1_out of ResNetFPN_8_2 (1/2 resolution, 128 ch) vs the oracle."""
+    from detectorfreesfm_b200 import B200LoFTR
+    m = B200LoFTR(util.loftr_config(fine=True)).cuda().eval()
+    m.load_state_dict(sd)
+    im = util.synth_image(hw[0], hw[1], seed=7)
+    x3, x1 = lo.resnet_fpn_8_2(im, sd, fine=True)
+    tokens, feat_f = m.extract_features(im.cuda())
+    ref_f = x1[0].flatten(1).t()
+    assert feat_f.shape == ref_f.shape
+    assert rel_err(feat_f.cpu(), ref_f) < 5e-5, rel_err(feat_f.cpu(), ref_f)
+    h, w = x3.shape[2:]
+    ref_c = (x3 + lo.position_encoding_sine(256, h, w)[None]).flatten(2).transpose(1, 2)[0]
+    assert rel_err(tokens.cpu(), ref_c) < 5e-5
+
+
+@pytest.mark.parametrize("temperature,thr", [(0.01, 0.2), (0.01, 0.0)])
+def test_end_to_end_coarse_fine(sd, temperature, thr):
+    """match type 'coarse_fine' (texturepoor config): fine-level keypoints within 0.1 px (north_star), expec_f within 1e-3."""
+    from detectorfreesfm_b200 import B200LoFTR
+    m = B200LoFTR(util.loftr_config(thr=thr, temperature=temperature, fine=True)).cuda().eval()
+    m.load_state_dict(sd)
+    im0, im1 = util.synth_pair(96, 128, seed=1)
+    scale0, scale1 = torch.tensor([[1.5, 1.25]]), torch.tensor([[1.0, 2.0]])
+    ref = lo.loftr_forward({"image0": im0, "image1": im1, "scale0": scale0, "scale1": scale1}, sd,
+                           {"thr": thr, "temperature": temperature, "fine_enable": True}, keep=True)
+    data = {"image0": im0.cuda(), "image1": im1.cuda(), "scale0": scale0.cuda(), "scale1": scale1.cuda()}
+    m(data)
+    assert len(ref["mconf"]) > 5
+    assert torch.equal(data["i_ids"].cpu(), ref["i_ids"]) and torch.equal(data["j_ids"].cpu(), ref["j_ids"])
+    assert (data["expec_f"].cpu() - ref["expec_f"]).abs().max().item() < 1e-3
+    assert torch.equal(data["mkpts0_f"].cpu(), ref["mkpts0_f"])
+    assert (data["mkpts1_f"].cpu() - ref["mkpts1_f"]).abs().max().item() < 0.1
+    assert (data["mkpts1_f"].cpu() - ref["mkpts1_f"]).abs().max().item() < 1e-2  # in practice ~1e-4 px

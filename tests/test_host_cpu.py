@@ -41,7 +41,12 @@ def test_no_cpu_fallback():
 def test_unsupported_configs_are_rejected():
     from detectorfreesfm_b200 import B200LoFTR
     from tests import util
+    cfg = util.loftr_config()
+    cfg["match_coarse"]["match_type"] = "sinkhorn"
+    with pytest.raises(NotImplementedError):
+        B200LoFTR(cfg)
     cfg = util.loftr_config(fine=True)
+    cfg["fine_window_size"] = 7
     with pytest.raises(NotImplementedError):
         B200LoFTR(cfg)
 
