@@ -703,7 +703,7 @@ void CoarseEngine::fine_match(const float* ff0, int Hf0, int Wf0, const float* f
     layer128(1, false, 0, MW, MW, MW, f.segs + M, M, f.segs + 2 * M, M, st);
     layer128(1, false, MW, MW, 0, MW, f.segs, M, f.segs + 3 * M, M, st);
     {   // FineMatching: centre token of window 0 against the 25 tokens of window 1, soft-argmax + std
-        const size_t smem = (static_cast<size_t>(1) * 128 + static_cast<size_t>(25) * 129 + static_cast<size_t>(kMaxViews) * 3) * sizeof(float);
+        const size_t smem = fine_match_smem_bytes(5, 1);
         DFSFM_CUDA(cudaMemsetAsync(coords_out, 0, static_cast<size_t>(M) * 2 * sizeof(float), st));
         LaunchScope ls("fine_match", st);
         fine_match_kernel<<<M, kFmThreads, smem, st>>>(f.xf, f.tracks, f.views, 1, 5, 1, f.d_query, coords_out, std_out, M);

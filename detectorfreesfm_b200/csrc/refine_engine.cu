@@ -364,7 +364,7 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
     // ---- window correlation + soft-argmax + reference-point search
     {
         const int L = LW_ * LW_;
-        const size_t smem = (static_cast<size_t>(L) * 128 + static_cast<size_t>(WW) * 129 + static_cast<size_t>(L) * kMaxViews * 3) * sizeof(float);
+        const size_t smem = fine_match_smem_bytes(W_, LW_);
         static bool configured = false;
         if (!configured) {
             DFSFM_CUDA(cudaFuncSetAttribute(fine_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -177,30 +177,39 @@ struct ViewRec {
 };
 constexpr int kMaxViews = 16;
 constexpr int kFmThreads = 256;
-// dynamic smem: ref[L][C] + qry[WW][C+1] + coords[L][kMaxViews][3]
+constexpr int kFmLB = 4;  // candidate reference points handled together by a warp (register tile)
+inline __host__ __device__ int fm_lpad(int L) { return ((L + kFmLB - 1) / kFmLB) * kFmLB; }
+inline size_t fine_match_smem_bytes(int W, int LW) {
+    const int WW = W * W, L = LW * LW;
+    return (static_cast<size_t>(128) * fm_lpad(L) + static_cast<size_t>(WW) * 129 + static_cast<size_t>(L) * kMaxViews * 3) * sizeof(float);
+}
+// dynamic smem: refT[C][Lpad] + qry[WW][C+1] + res[L][kMaxViews][3]
 static __global__ void __launch_bounds__(kFmThreads) fine_match_kernel(const float* __restrict__ tokens /*[T][128]*/,
                                                                        const TrackRec* __restrict__ tracks, const ViewRec* __restrict__ views,
                                                                        int Nq, int W, int LW, float* __restrict__ query_out /*[M][2]*/,
                                                                        float* __restrict__ ref_out /*[Nq][M][2]*/, float* __restrict__ std_out /*[Nq][M]*/,
                                                                        int M) {
     constexpr int C = 128;
-    extern __shared__ float sm[];
-    const int WW = W * W, L = LW * LW;
-    float* ref = sm;                     // [L][C]
-    float* qry = ref + L * C;            // [WW][C+1]
+    extern __shared__ __align__(16) float sm[];
+    const int WW = W * W, L = LW * LW, Lp = fm_lpad(L);
+    float* refT = sm;                    // [C][Lp]: candidate features, transposed so that 4 candidates are one float4
+    float* qry = refT + C * Lp;          // [WW][C+1]
     float* res = qry + WW * (C + 1);     // [L][kMaxViews][3] = (cx, cy, std)
     __shared__ int s_best;
     const int t = blockIdx.x;
     const TrackRec tr = tracks[t];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r0 = W / 2 - LW / 2;
-    for (int i = threadIdx.x; i < L * C; i += kFmThreads) {
+    for (int i = threadIdx.x; i < Lp * C; i += kFmThreads) {
         const int l = i / C, c = i - l * C;
-        const int ly = l / LW, lx = l - ly * LW;
-        ref[i] = tokens[(static_cast<long long>(tr.tok0) + (r0 + ly) * W + (r0 + lx)) * C + c];
+        float v = 0.f;
+        if (l < L) {
+            const int ly = l / LW, lx = l - ly * LW;
+            v = tokens[(static_cast<long long>(tr.tok0) + (r0 + ly) * W + (r0 + lx)) * C + c];
+        }
+        refT[c * Lp + l] = v;
     }
     const float inv_sqrt_c = 1.f / sqrtf(static_cast<float>(C));
-    const float step = 2.f / static_cast<float>(W - 1);
     for (int n = 0; n < tr.n_views; ++n) {
         __syncthreads();
         const float* q = tokens + (static_cast<long long>(tr.qtok0) + static_cast<long long>(n) * WW) * C;
@@ -209,59 +218,68 @@ static __global__ void __launch_bounds__(kFmThreads) fine_match_kernel(const flo
             qry[r * (C + 1) + c] = q[i];
         }
         __syncthreads();
-        for (int l = warp; l < L; l += kFmThreads / 32) {
-            float sim[8];  // W*W <= 225 -> at most 8 window cells per lane
-            float mx = -INFINITY;
+        for (int l0 = warp * kFmLB; l0 < L; l0 += (kFmThreads / 32) * kFmLB) {
+            float sim[kFmLB][8];  // W*W <= 225 -> at most 8 window cells per lane
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const int r = lane + 32 * k;
-                float acc = 0.f;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
                 if (r < WW) {
                     const float* qr = qry + r * (C + 1);
-                    const float* rf = ref + l * C;
+                    const float* rf = refT + l0;
 #pragma unroll 8
-                    for (int c = 0; c < C; ++c) acc = fmaf(rf[c], qr[c], acc);
-                    acc *= inv_sqrt_c;
-                    mx = fmaxf(mx, acc);
+                    for (int c = 0; c < C; ++c) {
+                        const float qv = qr[c];
+                        const float4 rv = *reinterpret_cast<const float4*>(rf + c * Lp);
+                        a0 = fmaf(rv.x, qv, a0); a1 = fmaf(rv.y, qv, a1); a2 = fmaf(rv.z, qv, a2); a3 = fmaf(rv.w, qv, a3);
+                    }
                 }
-                sim[k] = acc;
+                sim[0][k] = a0 * inv_sqrt_c; sim[1][k] = a1 * inv_sqrt_c; sim[2][k] = a2 * inv_sqrt_c; sim[3][k] = a3 * inv_sqrt_c;
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float se = 0.f, ex = 0.f, ey = 0.f, exx = 0.f, eyy = 0.f;
+            for (int li = 0; li < kFmLB; ++li) {
+                const int l = l0 + li;
+                if (l >= L) break;
+                float mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int r = lane + 32 * k;
-                if (r < WW) {
-                    const float e = expf(sim[k] - mx);
-                    const int ry = r / W, rx = r - ry * W;
-                    const float gx = (static_cast<float>(rx) / static_cast<float>(W - 1) - 0.5f) * 2.f;
-                    const float gy = (static_cast<float>(ry) / static_cast<float>(W - 1) - 0.5f) * 2.f;
-                    se += e;
-                    ex = fmaf(e, gx, ex);
-                    ey = fmaf(e, gy, ey);
-                    exx = fmaf(e, gx * gx, exx);
-                    eyy = fmaf(e, gy * gy, eyy);
+                for (int k = 0; k < 8; ++k)
+                    if (lane + 32 * k < WW) mx = fmaxf(mx, sim[li][k]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                float se = 0.f, ex = 0.f, ey = 0.f, exx = 0.f, eyy = 0.f;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int r = lane + 32 * k;
+                    if (r < WW) {
+                        const float e = expf(sim[li][k] - mx);
+                        const int ry = r / W, rx = r - ry * W;
+                        const float gx = (static_cast<float>(rx) / static_cast<float>(W - 1) - 0.5f) * 2.f;
+                        const float gy = (static_cast<float>(ry) / static_cast<float>(W - 1) - 0.5f) * 2.f;
+                        se += e;
+                        ex = fmaf(e, gx, ex);
+                        ey = fmaf(e, gy, ey);
+                        exx = fmaf(e, gx * gx, exx);
+                        eyy = fmaf(e, gy * gy, eyy);
+                    }
                 }
-            }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                se += __shfl_xor_sync(0xffffffffu, se, o);
-                ex += __shfl_xor_sync(0xffffffffu, ex, o);
-                ey += __shfl_xor_sync(0xffffffffu, ey, o);
-                exx += __shfl_xor_sync(0xffffffffu, exx, o);
-                eyy += __shfl_xor_sync(0xffffffffu, eyy, o);
-            }
-            if (lane == 0) {
-                const float cx = ex / se, cy = ey / se;
-                const float vx = exx / se - cx * cx, vy = eyy / se - cy * cy;
-                const float sd = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
-                float* o = res + (l * kMaxViews + n) * 3;
-                o[0] = cx; o[1] = cy; o[2] = sd;
+                for (int o = 16; o > 0; o >>= 1) {
+                    se += __shfl_xor_sync(0xffffffffu, se, o);
+                    ex += __shfl_xor_sync(0xffffffffu, ex, o);
+                    ey += __shfl_xor_sync(0xffffffffu, ey, o);
+                    exx += __shfl_xor_sync(0xffffffffu, exx, o);
+                    eyy += __shfl_xor_sync(0xffffffffu, eyy, o);
+                }
+                if (lane == 0) {
+                    const float cx = ex / se, cy = ey / se;
+                    const float vx = exx / se - cx * cx, vy = eyy / se - cy * cy;
+                    const float sd = sqrtf(fmaxf(vx, 1e-10f)) + sqrtf(fmaxf(vy, 1e-10f));
+                    float* o = res + (l * kMaxViews + n) * 3;
+                    o[0] = cx; o[1] = cy; o[2] = sd;
+                }
             }
         }
     }
-    (void)step;
     __syncthreads();
     if (threadIdx.x == 0) {
         int best = L / 2;
@@ -277,8 +295,9 @@ static __global__ void __launch_bounds__(kFmThreads) fine_match_kernel(const flo
         }
         s_best = best;
         const int bx = best % LW, by = best / LW;
-        const float ox = (static_cast<float>(bx) / static_cast<float>(LW - 1)) * 2.f - 1.f;
-        const float oy = (static_cast<float>(by) / static_cast<float>(LW - 1)) * 2.f - 1.f;
+        const float den = static_cast<float>(LW > 1 ? LW - 1 : 1);
+        const float ox = (static_cast<float>(bx) / den) * 2.f - 1.f;
+        const float oy = (static_cast<float>(by) / den) * 2.f - 1.f;
         query_out[t * 2 + 0] = tr.qx + ox * static_cast<float>(LW / 2) * tr.sqx;
         query_out[t * 2 + 1] = tr.qy + oy * static_cast<float>(LW / 2) * tr.sqy;
     }
