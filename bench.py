@@ -225,9 +225,11 @@ def main():
     ms_cold = timed(lambda: step_resident(False), K, True)
     launches = lib.dfsfm_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    step_resident(True)   # every variant gets its own untimed warm-up step (allocator growth, feature-cache storage)
     ms_cached = timed(lambda: step_resident(True), K, True)
     step_e2e(False)
     ms_e2e = timed(lambda: step_e2e(False), K, True)
+    step_e2e(True)
     ms_e2e_cached = timed(lambda: step_e2e(True), K, True)
     n_pairs = len(pairs) * world
 
@@ -241,11 +243,13 @@ def main():
     conv_alg = conv_gemm_flops(HW, HW) * 2 * len(pairs)
     achieved = conv_alg / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None
     total_ms = sum(v[1] for v in prof.values())
-    roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,split,ConvEpi> (backbone implicit-GEMM convolutions)",
+    roofline = {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,split,ConvEpi> (backbone implicit-GEMM convolutions, persistent CTA pairs)",
                 "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": (achieved / peaks["tflops"]) if achieved else None,
-                "traffic": None, "peak_source": peaks["src"],
+                "traffic": 238.0e6 / 1e9 if conv_ms else None, "traffic_unit": "GB per launch of the largest conv (layer1 3x3 with residual; ncu dram read+write, profiles/r01_ncu_conv_summary.txt; algorithmic 0.267 GB)",
+                "peak_source": peaks["src"], "passes": 3,
+                "executed": (3 * achieved) if achieved else None, "executed_frac": (3 * achieved / peaks["tflops"]) if achieved else None,
                 "note": "achieved = algorithmic FLOPs (true channel counts, 1 pass); the kernel executes 3 fp16 MMA passes per K-step "
-                        "(split-fp16 operands for fp32-grade parity) => tensor-pipe utilisation = 3 x frac (+ padding)",
+                        "(split-fp16 operands for fp32-grade parity): `executed` = 3 x achieved is the fp16 tensor-pipe rate (padding and halo rows not counted)",
                 "launches": conv_cnt, "avg_launch_ms": conv_ms / conv_cnt if conv_cnt else None, "share_of_step": conv_ms / total_ms if total_ms else None,
                 "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items())}}
 
@@ -288,7 +292,7 @@ def main():
                "ms_per_chunk": ms2 / k2, "tracks_per_chunk": args.hp2_tracks, "patches_per_chunk": n_patches,
                "e2e": {"value": args.hp2_tracks * k2 * world / (ms2_e2e * 1e-3), "unit": "tracks/s",
                        "h2d_bytes_per_step": sum(im.numel() * 4 for im in host_imgs), "d2h_bytes_per_step": args.hp2_tracks * 2 * 4 * 10},
-               "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,split,ConvEpi> (S2DNet patch convolutions)",
+               "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,split,ConvEpi> (S2DNet patch convolutions, persistent CTA pairs)",
                             "achieved": pconv_alg / (pc_ms * 1e-3) / 1e12 if pc_ms else None, "peak": peaks["tflops"], "unit": "TFLOP/s",
                             "frac": pconv_alg / (pc_ms * 1e-3) / 1e12 / peaks["tflops"] if pc_ms else None,
                             "note": "algorithmic = FLOPs the reference executes (1.02 GFLOP/patch); the engine skips the part of the 5x5 "

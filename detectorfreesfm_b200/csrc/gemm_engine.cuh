@@ -208,6 +208,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
+    // Programmatic dependent launch: let the next kernel of the stream start its prologue on SMs we leave idle ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -232,6 +234,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // ... and wait here, with barriers initialised and TMEM allocated, until the previous kernel's results are visible.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int n_iters = core.num_taps * core.kchunks;
 
     if (warp == 0) {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -111,6 +112,14 @@ inline int sm_count() {
     }
     return n;
 }
+inline bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 // engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
 template <int BN, bool kSplit, class Epi>
 inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
@@ -126,8 +135,18 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
     const int tiles = m_pairs * n_tiles;
     const int max_clusters = sm_count() / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
-    kern<<<dim3(2 * clusters), kGemm2Threads, Cfg::kSmemBytes, st>>>(maps, core, ep, tiles, n_tiles);
-    DFSFM_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kGemm2Threads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: overlap this kernel's prologue with the previous kernel's tail
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, core, ep, tiles, n_tiles));
 }
 
 // Fill the tap table of a stride-1 k x k convolution on a flat-halo geometry with row pitch Wp.
