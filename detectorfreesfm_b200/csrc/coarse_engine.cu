@@ -603,6 +603,11 @@ void CoarseEngine::layer128(int li, bool self, int x0, int xn, int s0, int sn, c
         e.out_hi = f.m1.hi + static_cast<long long>(x0) * 128; e.out_lo = f.m1.lo() + static_cast<long long>(x0) * 128; e.out_ld = 128;
         launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st, "fine_lin");
     }
+    if (fused_mlp_enabled()) {
+        launch_mlp128_fused(f.x, f.m1, x0, xn, params.mat(p + ".mlp0"), params.mat(p + ".mlp2"), params.vec(p + ".ln2.g"), params.vec(p + ".ln2.b"),
+                            f.xf, st);
+        return;
+    }
     {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(i == 1 ? f.m1 : f.x, x0, xn);

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "host_utils.h"
+#include "mlp_fused.cuh"
 #include "simt_kernels.cuh"
 
 namespace dfsfm {
@@ -56,6 +57,51 @@ inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, cons
     LaunchScope ls(label, st);
     if (engine_version() == 2) launch_gemm2<BN, kSplit, Epi>(maps, core, ep, n_total, st);
     else launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+}
+
+// Fused mlp.0 + ReLU + mlp.2 + norm2 + residual for d_model 128 (mlp_fused.cuh); DFSFM_FUSED_MLP=0 selects the two-GEMM path.
+inline bool fused_mlp_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_FUSED_MLP");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && engine_version() == 2;
+}
+inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long long T, const HL& w0, const HL& w2, const float* gamma,
+                                const float* beta, float* xf, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        DFSFM_CUDA(cudaFuncSetAttribute(mlp128_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemBytes));
+        configured = true;
+    }
+    MlpMaps maps;
+    maps.x = make_tmap(x.hi + row0 * 128, 128, T, x.plane_elems(), 128);
+    maps.m1 = make_tmap(m1.hi + row0 * 128, 128, T, m1.plane_elems(), 128);
+    maps.w0 = make_tmap(w0, 128);
+    maps.w2 = make_tmap(w2, 64);
+    MlpParams p;
+    p.T = static_cast<int>(T);
+    p.gamma = gamma; p.beta = beta;
+    p.xf = xf + row0 * 128;
+    p.x_hi = x.hi + row0 * 128;
+    p.x_lo = x.lo() + row0 * 128;
+    const int tiles = static_cast<int>((T + 2 * kBM - 1) / (2 * kBM));
+    const int max_clusters = sm_count() / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    LaunchScope ls("mlp_fused", st);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kMlpThreads);
+    cfg.dynamicSmemBytes = kMlpSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, mlp128_fused_kernel, maps, p, tiles));
 }
 
 // Packed parameters on the device: GEMM operands as split-fp16 [rows][cols], everything else as fp32.

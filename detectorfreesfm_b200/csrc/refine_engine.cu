@@ -188,6 +188,11 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
             e.out_hi = m1_.b.hi; e.out_lo = m1_.b.lo(); e.out_ld = 128;
             launch_gemm_counted<128, true, LinEpi>(maps, c, e, 128, st, "lin");
         }
+        if (fused_mlp_enabled()) {  // mlp.0 + relu + mlp.2 + norm2 + residual in one kernel: hid stays on the SM
+            launch_mlp128_fused(x_.b, m1_.b, 0, T, params.mat(p + ".mlp0"), params.mat(p + ".mlp2"), params.vec(p + ".ln2.g"),
+                                params.vec(p + ".ln2.b"), xf_.p, st);
+            continue;
+        }
         {   // mlp.0 on cat[x, message] + relu
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(i == 1 ? m1_.b : x_.b);
             maps.b = make_tmap(params.mat(p + ".mlp0"), bbox(256));

@@ -123,3 +123,25 @@ def test_end_to_end_coarse_fine(sd, temperature, thr):
     assert torch.equal(data["mkpts0_f"].cpu(), ref["mkpts0_f"])
     assert (data["mkpts1_f"].cpu() - ref["mkpts1_f"]).abs().max().item() < 0.1
     assert (data["mkpts1_f"].cpu() - ref["mkpts1_f"]).abs().max().item() < 1e-2  # in practice ~1e-4 px
+
+
+# ----------------------------------------------------------------------------------------------- edge cases
+def test_unequal_image_sizes_and_empty_match_set(sd):
+    """Different HxW per image (every demo image has its own size, loftr.py:48-49) and a threshold nothing passes."""
+    from detectorfreesfm_b200 import B200LoFTR
+    im0 = util.synth_image(96, 136, seed=11)
+    im1 = util.synth_image(120, 88, seed=12)
+    for thr, temp in ((0.0, 0.01), (1.0, 0.1)):
+        m = B200LoFTR(util.loftr_config(thr=thr, temperature=temp)).cuda().eval()
+        m.load_state_dict(sd)
+        ref = lo.loftr_forward({"image0": im0, "image1": im1}, sd, {"thr": thr, "temperature": temp}, keep=True)
+        data = {"image0": im0.cuda(), "image1": im1.cuda(), "_return_conf_matrix": True}
+        m(data)
+        assert tuple(data["hw0_c"]) == (12, 17) and tuple(data["hw1_c"]) == (15, 11)
+        assert (data["conf_matrix"].cpu() - ref["conf_matrix"]).abs().max().item() < 1e-3
+        assert torch.equal(data["i_ids"].cpu(), ref["i_ids"]) and torch.equal(data["j_ids"].cpu(), ref["j_ids"])
+        assert data["mkpts0_f"].shape == ref["mkpts0_f"].shape and data["mconf"].shape == ref["mconf"].shape
+        if thr == 1.0:
+            assert data["mkpts0_f"].shape == (0, 2) and data["m_bids"].shape == (0,)
+        else:
+            assert torch.equal(data["mkpts1_f"].cpu(), ref["mkpts1_f"])

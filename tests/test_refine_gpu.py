@@ -53,7 +53,7 @@ def test_crop_and_resize_matches_oracle(lib):
     assert torch.equal(crops.cpu(), ref)
 
 
-@pytest.mark.parametrize("W,LW,M,seed", [(15, 7, 48, 2), (11, 3, 40, 5), (15, 7, 130, 7)])
+@pytest.mark.parametrize("W,LW,M,seed", [(15, 7, 48, 2), (11, 3, 40, 5), (15, 7, 130, 7), (7, 3, 33, 9), (15, 7, 1, 3)])
 def test_refine_chunk(W, LW, M, seed):
     from detectorfreesfm_b200 import B200MultiviewMatcher
     sd = weights.multiview_state_dict(0)
