@@ -74,4 +74,5 @@ def test_refine_chunk(W, LW, M, seed):
     assert dq < 1e-3, f"reference-point move differs by {dq} px"
     assert dr < 1e-2, f"refined keypoints differ by {dr} px"
     assert ds < 1e-3, ds
-    assert r[~mask].abs().max().item() == 0 and s[~mask].abs().max().item() == 0
+    if (~mask).any():
+        assert r[~mask].abs().max().item() == 0 and s[~mask].abs().max().item() == 0
