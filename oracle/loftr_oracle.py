@@ -22,6 +22,10 @@ DEFAULT_CFG = {
     "thr": 0.2, "border_rm": 2, "temperature": 0.1,
     "fine_enable": False, "fine_window": 5, "fine_d_model": 128, "fine_nhead": 8,
     "fine_layer_names": ["self", "cross"],
+    # The reference always evaluates the 1/2-resolution FPN branch, even when fine.enable=False and its output is unused
+    # (resnet_fpn.py:110-118).  The oracle skips it by default (same results); the CPU-baseline legs of bench.py switch
+    # this on so that the timed work is exactly the reference's.
+    "compute_unused_fine_branch": False,
 }
 
 
@@ -265,13 +269,14 @@ def loftr_forward(data, sd, cfg=None, q=None, keep=False):
     im0, im1 = data["image0"], data["image1"]
     out = {"bs": im0.size(0), "hw0_i": tuple(im0.shape[2:]), "hw1_i": tuple(im1.shape[2:])}
     fine = cfg["fine_enable"]
+    run_fpn = fine or cfg["compute_unused_fine_branch"]
     if out["hw0_i"] == out["hw1_i"]:
-        fc, ff = resnet_fpn_8_2(torch.cat([im0, im1], 0), sd, fine, q)
+        fc, ff = resnet_fpn_8_2(torch.cat([im0, im1], 0), sd, run_fpn, q)
         feat_c0, feat_c1 = fc.split(out["bs"])
         feat_f0, feat_f1 = ff.split(out["bs"]) if fine else (None, None)
     else:
-        feat_c0, feat_f0 = resnet_fpn_8_2(im0, sd, fine, q)
-        feat_c1, feat_f1 = resnet_fpn_8_2(im1, sd, fine, q)
+        feat_c0, feat_f0 = resnet_fpn_8_2(im0, sd, run_fpn, q)
+        feat_c1, feat_f1 = resnet_fpn_8_2(im1, sd, run_fpn, q)
     out["hw0_c"], out["hw1_c"] = tuple(feat_c0.shape[2:]), tuple(feat_c1.shape[2:])
     if keep:
         out["backbone_c0"], out["backbone_c1"] = feat_c0, feat_c1
