@@ -42,8 +42,8 @@ void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
 // TensorFlow-style crop_and_resize forward (the reference's L0 native op):
 //   third_party/RoIAlign.pytorch/roi_align/src/cuda/crop_and_resize_kernel.cu:10-82 (semantics),
 //   roi_align/src/crop_and_resize.cpp:7-113 (CPU twin the oracle is checked against).
-// One CTA per (box, channel-group); the needed source rows are read with coalesced row segments, every output
-// element costs 4 cached loads and 3 lerps, outputs are written fully coalesced (NCHW rows of crop_w floats).
+// One CTA per box; consecutive threads take consecutive output elements (x fastest), so the NCHW crop is written fully
+// coalesced and the four bilinear taps of neighbouring threads fall into the same cache lines of the source rows.
 __global__ void __launch_bounds__(256) crop_and_resize_kernel(const float* __restrict__ image, int batch, int depth, int ih, int iw,
                                                               const float* __restrict__ boxes, const int* __restrict__ box_index,
                                                               float extrapolation, int ch, int cw, float* __restrict__ crops) {
