@@ -171,4 +171,34 @@ int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev
     });
 }
 
+// Tap-group ("slab") variant of the engine test hook: groups of 3 taps with consecutive shifts share one activation slab.
+int dfsfm_debug_gemm_slab(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts, int cpad,
+                          int bn, int bo_mode, float* out_dev, int M, int N, void* stream) {
+    using namespace dfsfm;
+    return guard([&] {
+        DFSFM_CHECK(taps >= 3 && taps <= kMaxTaps && taps % 3 == 0, "taps must be a multiple of 3");
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        const __half* a = static_cast<const __half*>(a_dev);
+        const __half* w = static_cast<const __half*>(w_dev);
+        TmapPack maps;
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(a, C, a_rows, a_rows * C, kSlabRows);
+        const long long ktot = static_cast<long long>(taps) * cpad;
+        maps.b = make_tmap(w, static_cast<int>(ktot), w_rows, w_rows * ktot, bn / 2);
+        GemmCore c;
+        memset(&c, 0, sizeof(c));
+        c.M = M;
+        c.num_taps = taps;
+        c.bo_mode = bo_mode;
+        set_k(c, cpad);
+        for (int t = 0; t < taps; ++t) { c.tap_map[t] = 0; c.tap_shift[t] = shifts[t]; }
+        ConvEpiParams e;
+        memset(&e, 0, sizeof(e));
+        e.M = M; e.N = N; e.out_mode = OUT_FLAT; e.out_f32 = out_dev; e.out_f32_ld = N;
+        LaunchScope ls("gemm_slab", st);
+        if (bn == 128) launch_gemm2<128, true, ConvEpi, 3>(maps, c, e, N, st);
+        else if (bn == 64) launch_gemm2<64, true, ConvEpi, 3>(maps, c, e, N, st);
+        else throw Error("unsupported bn for the slab variant");
+    });
+}
+
 }  // extern "C"

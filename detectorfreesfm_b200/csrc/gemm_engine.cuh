@@ -38,6 +38,7 @@ struct GemmCore {
     int k16_last;  // valid 16-wide K steps in the last chunk of a tap (1..4)
     int cpad;      // K elements per tap in the weight matrix
     int b_row0;    // first weight row (output channel) of this launch
+    int bo_mode;   // tap groups only: 1 = put (address >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
     int8_t tap_map[kMaxTaps];  // which activation map a tap reads
     int tap_shift[kMaxTaps];   // row shift of a tap
 };
@@ -173,10 +174,15 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
 // shared-memory traffic per MMA drops from (A + B) to (A + B/2) per SM.  Clusters loop over tiles (static round-robin);
 // the TMA producer runs ahead across tile boundaries and, when TMEM has room for two accumulator sets (BN <= 128 with
 // split operands), the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, bool kSplit, bool kSepCorr = true>
+// G = taps per group: G consecutive taps whose row shifts are consecutive (the dx = -1,0,1 taps of one kernel row) share ONE
+// activation slab of 128 + 8 rows per stage -- the tap's operand is the slab advanced by i rows (128 bytes) -- so the
+// activation traffic (L2 -> SM and TMA writes into shared memory) drops by G.
+constexpr int kSlabRows = kBM + 8;
+template <int BN, bool kSplit, bool kSepCorr = true, int G = 1>
 struct Gemm2Cfg {
-    static constexpr int kABytes = kBM * 128;
-    static constexpr int kBBytes = (BN / 2) * 128;  // this CTA's half of the weight tile
+    static constexpr int kABytes = (G == 1 ? kBM : kSlabRows) * 128;
+    static constexpr int kBTapBytes = (BN / 2) * 128;  // this CTA's half of one tap's weight tile
+    static constexpr int kBBytes = G * kBTapBytes;
     static constexpr int kPlanes = kSplit ? 2 : 1;
     static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
     static constexpr int kBudget = 204 * 1024;
@@ -195,11 +201,17 @@ struct Gemm2Cfg {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256 && (BN / 2) % 8 == 0, "invalid UMMA N for a CTA pair");
 };
 
-template <int BN, bool kSplit, class Epi>
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, int bo_mode) {
+    uint64_t d = make_smem_desc_sw128(smem_addr);
+    if (bo_mode) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
+    return d;
+}
+
+template <int BN, bool kSplit, class Epi, int G = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
                 const int n_tiles) {
-    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -236,7 +248,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     const uint32_t tmem_base = *tmem_slot;
     // ... and wait here, with barriers initialised and TMEM allocated, until the previous kernel's results are visible.
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const int n_iters = core.num_taps * core.kchunks;
+    const int n_iters = (core.num_taps / G) * core.kchunks;
 
     if (warp == 0) {
         if (lane == 0) {
@@ -247,19 +259,22 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                 const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
                 const int nrow = core.b_row0 + nt * BN + static_cast<int>(rank) * (BN / 2);
                 for (int it = 0; it < n_iters; ++it) {
-                    const int t = it / core.kchunks;
-                    const int c = it - t * core.kchunks;
+                    const int t = (it / core.kchunks) * G;  // first tap of the group
+                    const int c = it % core.kchunks;
                     mbar_wait(&empty_bar[s], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);
                     uint8_t* st = smem + s * Cfg::kStageBytes;
                     const CUtensorMap* am = &maps.a[core.tap_map[t]];
                     const int row = m0 + core.tap_shift[t];
-                    const int kb = t * core.cpad + c * kBK;
-                    tma_load_3d_2sm(st, am, &full_bar[s], c * kBK, row, 0);
+                    tma_load_3d_2sm(st, am, &full_bar[s], c * kBK, row, 0);  // G == 1: 128 rows; else the (128+8)-row slab
                     if (kSplit) tma_load_3d_2sm(st + Cfg::kABytes, am, &full_bar[s], c * kBK, row, 1);
                     uint8_t* sb = st + Cfg::kPlanes * Cfg::kABytes;
-                    tma_load_3d_2sm(sb, &maps.b, &full_bar[s], kb, nrow, 0);
-                    if (kSplit) tma_load_3d_2sm(sb + Cfg::kBBytes, &maps.b, &full_bar[s], kb, nrow, 1);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        const int kb = (t + i) * core.cpad + c * kBK;
+                        tma_load_3d_2sm(sb + i * Cfg::kBTapBytes, &maps.b, &full_bar[s], kb, nrow, 0);
+                        if (kSplit) tma_load_3d_2sm(sb + Cfg::kBBytes + i * Cfg::kBTapBytes, &maps.b, &full_bar[s], kb, nrow, 1);
+                    }
                     if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
                 }
             }
@@ -285,17 +300,22 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
                     const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
-                    for (int k = 0; k < nk; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(a_hi + k * 32);
-                        const uint64_t db = make_smem_desc_sw128(b_hi + k * 32);
-                        umma_f16_2sm(tmem_acc, da, db, idesc, acc);
-                        if (kSplit) {
-                            const uint64_t dal = make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32);
-                            const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + k * 32);
-                            umma_f16_2sm(tmem_corr, da, dbl, idesc, Epi::kSeparateCorr ? acc : 1u);
-                            umma_f16_2sm(tmem_corr, dal, db, idesc, 1);
+#pragma unroll
+                    for (int i = 0; i < G; ++i) {
+                        for (int k = 0; k < nk; ++k) {
+                            // tap i of the group reads the slab advanced by i rows (i * 128 bytes inside the swizzle atom)
+                            const uint64_t da = G == 1 ? make_smem_desc_sw128(a_hi + k * 32) : make_smem_desc_sw128_bo(a_hi + i * 128 + k * 32, core.bo_mode);
+                            const uint64_t db = make_smem_desc_sw128(b_hi + i * Cfg::kBTapBytes + k * 32);
+                            umma_f16_2sm(tmem_acc, da, db, idesc, acc);
+                            if (kSplit) {
+                                const uint64_t dal = G == 1 ? make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32)
+                                                            : make_smem_desc_sw128_bo(a_hi + Cfg::kABytes + i * 128 + k * 32, core.bo_mode);
+                                const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + i * Cfg::kBTapBytes + k * 32);
+                                umma_f16_2sm(tmem_corr, da, dbl, idesc, Epi::kSeparateCorr ? acc : 1u);
+                                umma_f16_2sm(tmem_corr, dal, db, idesc, 1);
+                            }
+                            acc = 1;
                         }
-                        acc = 1;
                     }
                     umma_commit_2sm(&empty_bar[s]);
                     if (++s == Cfg::kStages) { s = 0; phase ^= 1; }

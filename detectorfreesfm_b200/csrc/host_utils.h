@@ -121,10 +121,16 @@ inline bool pdl_enabled() {
     return v == 1;
 }
 // engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
-template <int BN, bool kSplit, class Epi>
+template <int BN, bool kSplit, class Epi, int G = 1>
 inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
-    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr>;
-    auto kern = gemm_tc2_kernel<BN, kSplit, Epi>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G>;
+    auto kern = gemm_tc2_kernel<BN, kSplit, Epi, G>;
+    if (G > 1) {
+        DFSFM_CHECK(core.num_taps % G == 0, "tap groups need num_taps divisible by the group size");
+        for (int t = 0; t < core.num_taps; ++t)
+            DFSFM_CHECK(core.tap_map[t] == core.tap_map[(t / G) * G] && core.tap_shift[t] == core.tap_shift[(t / G) * G] + t % G,
+                        "taps of a group must read the same map at consecutive row shifts");
+    }
     static bool configured = false;
     if (!configured) {
         DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));

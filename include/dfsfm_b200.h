@@ -96,6 +96,9 @@ int dfsfm_refine_chunk(dfsfm_refine_t* h, int n_img, const float* const* images_
  * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */
 int dfsfm_debug_gemm(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts,
                      int cpad, int bn, int split, float* out_dev, int M, int N, void* stream);
+/* Same for the tap-group variant (groups of 3 taps with consecutive row shifts share one activation slab); bn in {64,128}. */
+int dfsfm_debug_gemm_slab(const void* a_dev, int64_t a_rows, int C, const void* w_dev, int64_t w_rows, int taps, const int32_t* shifts,
+                          int cpad, int bn, int bo_mode, float* out_dev, int M, int N, void* stream);
 /* GEMM engine variant: 2 = persistent CTA pairs (cta_group::2, default), 1 = one CTA per output tile.  Test hook. */
 void dfsfm_set_engine(int version);
 int dfsfm_get_engine(void);
