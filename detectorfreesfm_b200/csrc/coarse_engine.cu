@@ -157,13 +157,20 @@ void CoarseEngine::free_feat(FeatWs& w) {
 template <int BN>
 void CoarseEngine::conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st) {
     const HL& w = params.mat(wname + ".w");
+    const bool slab = BN <= 128 && slab_applicable(core, n_in);
     TmapPack maps;
-    for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(ins[i < n_in ? i : 0], kBM);
+    for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = make_tmap(ins[i < n_in ? i : 0], slab ? kSlabRows : kBM);
     maps.b = make_tmap(w, bbox(BN));
     core.b_row0 = 0;
     DFSFM_CHECK(static_cast<long long>(core.num_taps) * core.cpad == w.C, "weight K does not match taps*cpad for " + wname);
     ep.M = core.M;
     ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
+    if constexpr (BN <= 128) {
+        if (slab) {
+            launch_gemm_slab_counted<BN, ConvEpi>(maps, core, ep, ep.N, st, "conv");
+            return;
+        }
+    }
     launch_gemm_counted<BN, true, ConvEpi>(maps, core, ep, ep.N, st, "conv");
 }
 

@@ -104,6 +104,28 @@ inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long 
     DFSFM_CUDA(cudaLaunchKernelEx(&cfg, mlp128_fused_kernel, maps, p, tiles));
 }
 
+// 3x3 stride-1 convolutions with BN <= 128: the three dx taps of a kernel row share one activation slab (engine 2 only).
+inline bool slab_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_SLAB");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && engine_version() == 2;
+}
+inline bool slab_applicable(const GemmCore& c, int n_in) {
+    if (!slab_enabled() || n_in != 1 || c.num_taps != 9) return false;
+    for (int t = 0; t < 9; ++t)
+        if (c.tap_map[t] != 0 || c.tap_shift[t] != c.tap_shift[(t / 3) * 3] + t % 3) return false;
+    return true;
+}
+template <int BN, class Epi>
+inline void launch_gemm_slab_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st,
+                                     const char* label) {
+    LaunchScope ls(label, st);
+    launch_gemm2<BN, true, Epi, 3>(maps, core, ep, n_total, st);
+}
+
 // Packed parameters on the device: GEMM operands as split-fp16 [rows][cols], everything else as fp32.
 class ParamStore {
   public:

@@ -131,13 +131,19 @@ void RefineEngine::conv(const HL& in, const PGeom& g, long long P, int taps_k, i
     conv_taps_s1(c, taps_k, g.Wp);
     DFSFM_CHECK(static_cast<long long>(c.num_taps) * cpad == w.C, "weight K mismatch for " + wname);
     TmapPack maps;
-    HL a = in;
-    a.rows = rows;  // the tensor map covers exactly the rows in use (OOB rows read as zero)
-    CUtensorMap am = make_tmap(a.hi, a.C, rows, in.plane_elems(), kBM);
+    const bool slab = BN <= 128 && slab_applicable(c, 1);
+    // the tensor map covers exactly the rows in use (OOB rows read as zero)
+    CUtensorMap am = make_tmap(in.hi, in.C, rows, in.plane_elems(), slab ? kSlabRows : kBM);
     for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = am;
     maps.b = make_tmap(w, bbox(BN));
     ep.M = c.M;
     ep.bias = params.has_vec(wname + ".b") ? params.vec(wname + ".b") : nullptr;
+    if constexpr (BN <= 128) {
+        if (slab) {
+            launch_gemm_slab_counted<BN, ConvEpi>(maps, c, ep, ep.N, st, "pconv");
+            return;
+        }
+    }
     launch_gemm_counted<BN, true, ConvEpi>(maps, c, ep, ep.N, st, "pconv");
 }
 
