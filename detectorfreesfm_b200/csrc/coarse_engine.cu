@@ -409,7 +409,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
         { LaunchScope ls("kv", st);
           kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
                                                                       kKvTokPerCta); }
-        { LaunchScope ls("kv", st);
+        { LaunchScope ls("kv_final", st);
           kv_final_kernel<32><<<dim3((256 * 33 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
                                                                                    tok_.kv_state, kKvTokPerCta); }
         { LaunchScope ls("attn", st);
