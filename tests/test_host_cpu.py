@@ -106,3 +106,26 @@ def test_partition_and_gather_gloo_world2():
         assert p.exitcode == 0
     assert flat == [(i, i + 1) for i in range(7)]  # every unit arrived once, with its rows
     assert t == 2.0 and lens == [4, 3]
+
+
+def test_refinement_window_rescale_matches_reference_rule():
+    """multiview_match_worker.py:20-34: window 15 -> 11 -> 7 (floor 7), left window 7 -> 3 (floor 3) per refinement iteration."""
+    from detectorfreesfm_b200.plugin import rescale_windows
+    from tests.test_refine_gpu import multiview_config
+    cfg = multiview_config(15, 7)
+    got = []
+    for factor in (None, 0, 2, 4, 6):
+        r = rescale_windows(cfg, factor)
+        got.append((r["multiview_transform"]["window_size"], r["backbone"]["s2dnet"]["window_size"],
+                    r["multiview_matching_test"]["window_size"], r["multiview_matching_test"]["left_point_movement_window_size"]))
+    assert got == [(15, 15, 15, 7), (15, 15, 15, 7), (11, 11, 11, 3), (7, 7, 7, 3), (7, 7, 7, 3)]
+    assert cfg["multiview_transform"]["window_size"] == 15  # the input config is not mutated
+
+
+def test_shard_covers_every_unit_once():
+    from detectorfreesfm_b200.dist import shard
+    for n, world in ((5050, 8), (28, 8), (3, 8), (500, 4)):
+        seen = sorted(i for r in range(world) for i in shard(n, r, world))
+        assert seen == list(range(n))
+        sizes = [len(shard(n, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
