@@ -110,6 +110,24 @@ class CoarseEngine {
     void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st);
 };
 
+static int kv_tok() {  // tokens per KV-partial CTA (A/B: DFSFM_KV_TOK)
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("DFSFM_KV_TOK");
+        v = e ? atoi(e) : kKvTokPerCta;
+        if (v < 16) v = 16;
+    }
+    return v;
+}
+static bool lin_bn128() {  // A/B switch: 128-wide N tiles for the wide linears (QKV, KV, mlp.0): twice the tiles, better last-round fill
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_LIN_BN128");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+}
+
 static ParityBuf parity_alloc(long long rows, int C) {
     ParityBuf p;
     p.rows = rows;
@@ -358,7 +376,7 @@ void CoarseEngine::ensure_tok(int n) {
         DFSFM_CUDA(cudaMalloc(&tok_.stat[s], static_cast<size_t>(cap) * sizeof(float)));
         DFSFM_CUDA(cudaMalloc(&tok_.best[s], static_cast<size_t>(cap) * sizeof(unsigned long long)));
     }
-    tok_.kv_chunks = (cap + kKvTokPerCta - 1) / kKvTokPerCta;
+    tok_.kv_chunks = (cap + kv_tok() - 1) / kv_tok();
     DFSFM_CUDA(cudaMalloc(&tok_.xf, static_cast<size_t>(cap) * 256 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(2) * tok_.kv_chunks * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(2) * 256 * 33 * sizeof(float)));
@@ -392,7 +410,8 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
             c.M = xn; c.b_row0 = 0;
             e.M = xn; e.N = 768; e.elu_cols = 512; e.out_f32 = qkv + static_cast<long long>(x0) * 768; e.out_col0 = 0;
-            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
+            if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c, e, 768, st, "lin"); }
+            else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
         } else {
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
             c.M = xn; c.b_row0 = 0;
@@ -401,17 +420,18 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], s0, sn);
             c.M = sn; c.b_row0 = 256;
             e.M = sn; e.N = 512; e.elu_cols = 256; e.out_f32 = qkv + static_cast<long long>(s0) * 768; e.out_col0 = 256;
-            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
+            if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c, e, 512, st, "lin"); }
+            else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
         }
     }
     {   // KV state(s): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
-        const int chunks = (max_count + kKvTokPerCta - 1) / kKvTokPerCta;
+        const int chunks = (max_count + kv_tok() - 1) / kv_tok();
         { LaunchScope ls("kv", st);
           kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
-                                                                      kKvTokPerCta); }
+                                                                      kv_tok()); }
         { LaunchScope ls("kv_final", st);
           kv_final_kernel<32><<<dim3((256 * 33 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
-                                                                                   tok_.kv_state, kKvTokPerCta); }
+                                                                                   tok_.kv_state, kv_tok()); }
         { LaunchScope ls("attn", st);
           attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<32>(), st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
                                                                                     tok_.msg[0].hi, tok_.msg[0].lo(), 256); }
@@ -439,7 +459,8 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
         memset(&e, 0, sizeof(e));
         e.M = xn; e.N = 512; e.mode = LIN_RELU_HL;
         e.out_hi = tok_.hid[0].hi + static_cast<long long>(x0) * 512; e.out_lo = tok_.hid[0].lo() + static_cast<long long>(x0) * 512; e.out_ld = 512;
-        launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st, "lin");
+        if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".mlp0"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c2, e, 512, st, "lin"); }
+        else launch_gemm_counted<256, true, LinEpi>(maps, c2, e, 512, st, "lin");
     }
     // mlp.2 + norm2 + residual
     {
