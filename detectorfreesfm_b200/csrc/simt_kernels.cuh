@@ -106,8 +106,11 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
     constexpr int C = 8 * D;
     constexpr int C4 = C / 4;
     constexpr int SUB = 16;
-    __shared__ __align__(16) float Ks[SUB][C];
-    __shared__ __align__(16) float Vs[SUB][C];
+    // one buffer: the K / V staging tiles during the reduction, then the [C][D+1] result for a coalesced write-out
+    constexpr int kBuf = C * (D + 1) > 2 * SUB * C ? C * (D + 1) : 2 * SUB * C;
+    __shared__ __align__(16) float buf[kBuf];
+    float (*Ks)[C] = reinterpret_cast<float (*)[C]>(buf);
+    float (*Vs)[C] = reinterpret_cast<float (*)[C]>(buf + SUB * C);
     const Seg sg = segs[blockIdx.y];
     const int tid = threadIdx.x;
     const int h = tid / D;
@@ -159,10 +162,13 @@ static __global__ void __launch_bounds__(8 * D) kv_partial_kernel(const float* _
             }
         }
     }
-    float* o = part + (static_cast<long long>(blockIdx.y) * max_chunks + blockIdx.x) * (C * (D + 1)) + tid * (D + 1);
+    __syncthreads();  // every thread is done reading the staging tiles
 #pragma unroll
-    for (int v = 0; v < D; ++v) o[v] = acc[v];
-    o[D] = ksum;
+    for (int v = 0; v < D; ++v) buf[tid * (D + 1) + v] = acc[v];  // stride D+1: conflict-free
+    buf[tid * (D + 1) + D] = ksum;
+    __syncthreads();
+    float* o = part + (static_cast<long long>(blockIdx.y) * max_chunks + blockIdx.x) * (C * (D + 1));
+    for (int i = tid; i < C * (D + 1); i += C) o[i] = buf[i];  // coalesced
 }
 // state[seg.state][8*D*(D+1)] = sum over chunks in a fixed order (deterministic).  grid (ceil(SZ/64), segments); block
 // (64 outputs x 4 chunk groups): each group sums every 4th chunk, the 4 partial sums are combined through shared memory.
