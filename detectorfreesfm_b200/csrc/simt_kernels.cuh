@@ -201,7 +201,7 @@ static __global__ void __launch_bounds__(kKvFinalThreads) kv_final_kernel(const 
 // The warp's 4 query rows are staged in shared memory (coalesced float4 loads issued up front) and read back as broadcast
 // float4 -- per 16 FMAs the inner loop issues 4 state loads + 4 query loads instead of 16 + 16 shuffles.
 // Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
-constexpr int kAttnTokPerCta = 32;
+constexpr int kAttnTokPerCta = 128;  // 8 warps x 4 rounds x 4 tokens: the KV state is loaded once per 128 tokens
 template <int D>
 constexpr int attn_smem_bytes() { return (8 * D * (D + 1) + 8 * 4 * 8 * D) * static_cast<int>(sizeof(float)); }
 template <int D>
@@ -218,8 +218,16 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
     const Seg sg = segs[blockIdx.y];
     if (blockIdx.x * kAttnTokPerCta >= sg.count) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tw = blockIdx.x * kAttnTokPerCta + warp * TPW;
     float* qw = qs + warp * TPW * C;
+    for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
+    __syncthreads();
+    const int hs = lane / D, v = lane - hs * D;  // D == 32: hs = 0, v = lane
+    const float len = static_cast<float>(sg.count);
+#pragma unroll 1
+    for (int rep = 0; rep < kAttnTokPerCta / (8 * TPW); ++rep) {
+    const int tw = blockIdx.x * kAttnTokPerCta + (rep * 8 + warp) * TPW;
+    if (tw >= sg.count) break;
+    __syncwarp();
     {   // stage this warp's query rows (zeros for masked / out-of-range tokens)
         constexpr int F4 = TPW * C / 4;
         for (int i = lane; i < F4; i += 32) {
@@ -230,10 +238,7 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
             *reinterpret_cast<float4*>(qw + ti * C + c4 * 4) = v;
         }
     }
-    for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
-    __syncthreads();
-    const int hs = lane / D, v = lane - hs * D;  // D == 32: hs = 0, v = lane
-    const float len = static_cast<float>(sg.count);
+    __syncwarp();
 #pragma unroll 1
     for (int j = 0; j < NJ; ++j) {
         const int h = (32 * j) / D + hs;
@@ -271,6 +276,7 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
             }
         }
     }
+    }  // rep
 }
 
 // --------------------------------------------------------------------------------------------------------
