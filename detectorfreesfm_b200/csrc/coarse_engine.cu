@@ -433,8 +433,8 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
           kv_final_kernel<32><<<dim3((256 * 33 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
                                                                                    tok_.kv_state, kv_tok()); }
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<32><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<32>(), st>>>(qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state,
-                                                                                    tok_.msg[0].hi, tok_.msg[0].lo(), 256); }
+          attn_apply_kernel<32><<<dim3((max_count + kAttnTokCoarse - 1) / kAttnTokCoarse, n_segs), 256, attn_smem_bytes<32>(), st>>>(
+              qkv, 768, tok_.seg_dev + apply_seg0, tok_.kv_state, tok_.msg[0].hi, tok_.msg[0].lo(), 256, kAttnTokCoarse); }
         DFSFM_CUDA(cudaGetLastError());
     }
     c.M = xn; c.b_row0 = 0;
@@ -619,7 +619,7 @@ void CoarseEngine::layer128(int li, bool self, int x0, int xn, int s0, int sn, c
     { LaunchScope ls("fine_kv", st);
       kv_final_kernel<16><<<dim3((8 * 16 * 17 + 63) / 64, n_kv), kKvFinalThreads, 0, st>>>(f.kvpart, kv_segs, 1, f.kvstate, 32); }
     { LaunchScope ls("fine_attn", st);
-      attn_apply_kernel<16><<<dim3(1, n_apply), 256, attn_smem_bytes<16>(), st>>>(f.qkv, 384, apply_segs, f.kvstate, f.msg.hi, f.msg.lo(), 128); }
+      attn_apply_kernel<16><<<dim3(1, n_apply), 256, attn_smem_bytes<16>(), st>>>(f.qkv, 384, apply_segs, f.kvstate, f.msg.hi, f.msg.lo(), 128, 32); }
     DFSFM_CUDA(cudaGetLastError());
     c.M = xn; c.b_row0 = 0;
     {

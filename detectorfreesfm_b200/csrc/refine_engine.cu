@@ -182,8 +182,8 @@ void RefineEngine::transformer(long long T, int n_segs, int max_count, cudaStrea
         // self: a segment reads its own state; cross: its partner's -- both directions use the PRE-update tokens
         // (matcher_module/transformer.py:162-167), which is what a single q/k/v pass over the old tokens gives.
         { LaunchScope ls("attn", st);
-          attn_apply_kernel<16><<<dim3((max_count + kAttnTokPerCta - 1) / kAttnTokPerCta, n_segs), 256, attn_smem_bytes<16>(), st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
-                                                                                  msg_.b.hi, msg_.b.lo(), 128); }
+          attn_apply_kernel<16><<<dim3((max_count + kAttnTokRefine - 1) / kAttnTokRefine, n_segs), 256, attn_smem_bytes<16>(), st>>>(qkv_.p, 384, self ? segs_self : segs_cross, kvstate_.p,
+                                                                                  msg_.b.hi, msg_.b.lo(), 128, kAttnTokRefine); }
         DFSFM_CUDA(cudaGetLastError());
         {   // merge + norm1
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = amap(msg_.b);

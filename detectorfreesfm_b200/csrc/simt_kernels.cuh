@@ -201,13 +201,15 @@ static __global__ void __launch_bounds__(kKvFinalThreads) kv_final_kernel(const 
 // The warp's 4 query rows are staged in shared memory (coalesced float4 loads issued up front) and read back as broadcast
 // float4 -- per 16 FMAs the inner loop issues 4 state loads + 4 query loads instead of 16 + 16 shuffles.
 // Masked query tokens (index >= seg.valid) produce 0 (the reference multiplies Q by the mask).
-constexpr int kAttnTokPerCta = 128;  // 8 warps x 4 rounds x 4 tokens: the KV state is loaded once per 128 tokens
+// tokens per CTA (a multiple of 32): the KV state is loaded once per CTA; few big segments (HP-1) want many small CTAs,
+// thousands of short segments (HP-2) want the state load amortised.
+constexpr int kAttnTokCoarse = 32, kAttnTokRefine = 128;
 template <int D>
 constexpr int attn_smem_bytes() { return (8 * D * (D + 1) + 8 * 4 * 8 * D) * static_cast<int>(sizeof(float)); }
 template <int D>
 static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __restrict__ Q, int ldq, const Seg* __restrict__ segs,
                                                           const float* __restrict__ state, __half* __restrict__ out_hi,
-                                                          __half* __restrict__ out_lo, int ldo) {
+                                                          __half* __restrict__ out_lo, int ldo, int tok_per_cta) {
     constexpr int C = 8 * D;
     constexpr int SZ = C * (D + 1);
     constexpr int NJ = C / 32;  // output channels per lane
@@ -216,7 +218,7 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
     float* st = attn_sm;             // [C][D+1]: KV[h][d][v] at (h*D+d)*(D+1)+v, Ksum at +D
     float* qs = attn_sm + SZ;        // [8 warps][TPW][C]
     const Seg sg = segs[blockIdx.y];
-    if (blockIdx.x * kAttnTokPerCta >= sg.count) return;
+    if (blockIdx.x * tok_per_cta >= sg.count) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* qw = qs + warp * TPW * C;
     for (int i = threadIdx.x; i < SZ; i += 256) st[i] = state[static_cast<long long>(sg.state) * SZ + i];
@@ -224,8 +226,8 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
     const int hs = lane / D, v = lane - hs * D;  // D == 32: hs = 0, v = lane
     const float len = static_cast<float>(sg.count);
 #pragma unroll 1
-    for (int rep = 0; rep < kAttnTokPerCta / (8 * TPW); ++rep) {
-    const int tw = blockIdx.x * kAttnTokPerCta + (rep * 8 + warp) * TPW;
+    for (int rep = 0; rep < tok_per_cta / (8 * TPW); ++rep) {
+    const int tw = blockIdx.x * tok_per_cta + (rep * 8 + warp) * TPW;
     if (tw >= sg.count) break;
     __syncwarp();
     {   // stage this warp's query rows (zeros for masked / out-of-range tokens)
