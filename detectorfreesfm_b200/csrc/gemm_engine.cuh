@@ -158,7 +158,7 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0, 0, BN,
-                                             static_cast<int>(blockIdx.y));
+                                             static_cast<int>(blockIdx.y), nullptr);
         tc_fence_before();
     }
     __syncthreads();
@@ -178,17 +178,22 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
 // activation slab of 128 + 8 rows per stage -- the tap's operand is the slab advanced by i rows (128 bytes) -- so the
 // activation traffic (L2 -> SM and TMA writes into shared memory) drops by G.
 constexpr int kSlabRows = kBM + 8;
-template <int BN, bool kSplit, bool kSepCorr = true, int G = 1>
+template <int BN, bool kSplit, bool kSepCorr = true, int G = 1, int kEpiStageBytes = 0>
 struct Gemm2Cfg {
     static constexpr int kABytes = (G == 1 ? kBM : kSlabRows) * 128;
     static constexpr int kBTapBytes = (BN / 2) * 128;  // this CTA's half of one tap's weight tile
     static constexpr int kBBytes = G * kBTapBytes;
     static constexpr int kPlanes = kSplit ? 2 : 1;
     static constexpr int kStageBytes = kPlanes * (kABytes + kBBytes);
-    static constexpr int kBudget = 204 * 1024;
+    // per-warp epilogue staging (Epi::kEpiStageBytes: the warp's 32-row block is transposed through shared memory so that global
+    // loads / stores of the epilogue are row-contiguous); it comes out of the operand-stage budget only when it has to
+    static constexpr int kEpiSmem = kEpiStageBytes * kGemm2EpiWarps;
+    static constexpr int kBudgetMax = 227 * 1024 - 1024 - 256 - kEpiSmem;
+    static constexpr int kBudget = kBudgetMax < 204 * 1024 ? kBudgetMax : 204 * 1024;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kEpiOff = kStages * kStageBytes + 256;  // after the barriers
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiSmem;
     static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     // kSepCorr: hi*lo + lo*hi go to their own accumulator (long-K convolutions).  Short-K linears fold them into the main
     // accumulator (truncation bias ~ -5.5e-9*K*3 relative: harmless at K <= 512), which leaves TMEM room for a second
@@ -211,7 +216,7 @@ template <int BN, bool kSplit, class Epi, int G = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
                 const int n_tiles) {
-    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G, Epi::kEpiStageBytes>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -338,7 +343,8 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             mbar_wait(&tmem_full_bar[a], aphase);
             tc_fence_after();
             Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
-                                                 nt * BN, cb, ce, nt * 2 + half);
+                                                 nt * BN, cb, ce, nt * 2 + half,
+                                                 Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + (warp - 2) * Epi::kEpiStageBytes : nullptr);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
@@ -421,8 +427,9 @@ struct ConvEpiParams {
 struct ConvEpi {
     using Params = ConvEpiParams;
     static constexpr bool kSeparateCorr = true;
+    static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, uint8_t* stg) {
         const int row = row0 + lane;
         bool valid = row < p.M;
         int n_img = 0, y = 0, x = 0;
@@ -568,8 +575,10 @@ struct LinEpiParams {
 struct LinEpi {
     using Params = LinEpiParams;
     static constexpr bool kSeparateCorr = false;
+    static constexpr int kEpiStageBytes = 4096;  // engine 2: one 32 x 32 fp32 block per epilogue warp
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx,
+                                               uint8_t* stg) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         float mean = 0.f, rstd = 0.f;
@@ -588,6 +597,10 @@ struct LinEpi {
             const float md = s1 * inv_n;
             mean = pivot + md;
             rstd = rsqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
+        }
+        if (stg != nullptr) {
+            run_staged<kCorr>(p, tmem_warp, row0, lane, n0, cb, ce, mean, rstd, stg);
+            return;
         }
 #pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
@@ -643,6 +656,79 @@ struct LinEpi {
             }
         }
     }
+
+    // Engine-2 path.  A thread owns one accumulator ROW (a TMEM lane), so writing results straight from registers makes every
+    // warp-wide store touch 32 different cache lines (one per row): the L1 tag stage then costs 32 cycles per instruction and
+    // the short-K linears become epilogue-bound.  Here each 32 x 32 block is transposed through a 4 KB swizzled staging
+    // buffer (16-byte chunk index XOR row % 8: conflict-free both ways); afterwards lane l owns columns 4*(l%8)..+3 of rows
+    // 4*i + l/8, i = 0..7, so a warp-wide access covers four full 128-byte rows -- residual loads and all stores coalesce.
+    template <int kCorr>
+    static __device__ __forceinline__ void run_staged(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, float mean,
+                                                      float rstd, uint8_t* stg) {
+        const int ch = lane & 7, rsub = lane >> 3;
+        uint8_t* st_row = stg + lane * 128;
+        const int sw_w = lane & 7;
+#pragma unroll 1
+        for (int c0 = cb; c0 < ce; c0 += 32) {
+            const int nb = n0 + c0;
+            if (nb >= p.N) break;  // warp-uniform
+            const int col = nb + 4 * ch;
+            float4 res[8];
+            if (p.mode == LIN_LN && p.resid) {  // issue the residual loads before waiting on TMEM
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = row0 + 4 * i + rsub;
+                    res[i] = r < p.M ? *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(r) * p.resid_ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            float v[32];
+            load_acc32<kCorr>(tmem_warp + c0, v);
+            if (p.mode == LIN_LN) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                *reinterpret_cast<float4*>(st_row + ((q ^ sw_w) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            __syncwarp();
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.mode == LIN_LN) {
+                g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+                b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col));
+            }
+            const bool elu = p.mode == LIN_F32_ELU && nb < p.elu_cols;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int rl = 4 * i + rsub;
+                const int r = row0 + rl;
+                float4 w = *reinterpret_cast<const float4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
+                if (r >= p.M) continue;
+                if (p.mode == LIN_F32_ELU) {
+                    if (elu) {
+                        w.x = w.x > 0.f ? w.x + 1.f : fast_ex2(w.x * 1.4426950408889634f);  // elu(x) + 1 == exp(x), x <= 0
+                        w.y = w.y > 0.f ? w.y + 1.f : fast_ex2(w.y * 1.4426950408889634f);
+                        w.z = w.z > 0.f ? w.z + 1.f : fast_ex2(w.z * 1.4426950408889634f);
+                        w.w = w.w > 0.f ? w.w + 1.f : fast_ex2(w.w * 1.4426950408889634f);
+                    }
+                } else if (p.mode == LIN_RELU_HL) {
+                    w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
+                } else {
+                    w.x = w.x * g4.x + b4.x; w.y = w.y * g4.y + b4.y; w.z = w.z * g4.z + b4.z; w.w = w.w * g4.w + b4.w;
+                    if (p.resid) { w.x += res[i].x; w.y += res[i].y; w.z += res[i].z; w.w += res[i].w; }
+                }
+                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(r) * p.out_f32_ld + p.out_col0 + col) = w;
+                if (p.out_hi) {
+                    uint2 uh, ul;
+                    __half* hh = reinterpret_cast<__half*>(&uh);
+                    __half* hl = reinterpret_cast<__half*>(&ul);
+                    split_f16(w.x, hh[0], hl[0]); split_f16(w.y, hh[1], hl[1]); split_f16(w.z, hh[2], hl[2]); split_f16(w.w, hh[3], hl[3]);
+                    *reinterpret_cast<uint2*>(p.out_hi + static_cast<long long>(r) * p.out_ld + col) = uh;
+                    *reinterpret_cast<uint2*>(p.out_lo + static_cast<long long>(r) * p.out_ld + col) = ul;
+                }
+            }
+            __syncwarp();
+        }
+    }
 };
 
 // ------------------------------------------------------------------- dual-softmax similarity epilogues
@@ -672,8 +758,9 @@ __device__ __forceinline__ unsigned long long pack_best(float conf, int idx) {
 struct SimEpi {
     using Params = SimEpiParams;
     static constexpr bool kSeparateCorr = false;
+    static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, uint8_t* stg) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         if (p.mode == SIM_STATS) {

@@ -123,7 +123,7 @@ inline bool pdl_enabled() {
 // engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
 template <int BN, bool kSplit, class Epi, int G = 1>
 inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
-    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G>;
+    using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G, Epi::kEpiStageBytes>;
     auto kern = gemm_tc2_kernel<BN, kSplit, Epi, G>;
     if (G > 1) {
         DFSFM_CHECK(core.num_taps % G == 0, "tap groups need num_taps divisible by the group size");
