@@ -388,6 +388,16 @@ void CoarseEngine::ensure_tok(int n) {
 // One LoFTREncoderLayer.forward (transformer.py:35-58) on the token rows [x0, x0+xn) of the joint token array (image 0 at rows
 // [0,L), image 1 at [L,L+S)).  `self`: source == x (both images in one call, two attention segments); otherwise the source
 // rows are [s0, s0+sn).  kv_segs / apply_segs index the 6-entry device table built in transformer().
+// DFSFM_RES_HL=0: keep a separate fp32 residual stream (A/B switch; engine 1 always does)
+static bool res_hl() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_RES_HL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && engine_version() == 2;
+}
+
 void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count,
                               cudaStream_t st) {
     const std::string p = "tr." + std::to_string(li);
@@ -472,8 +482,15 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
         memset(&e, 0, sizeof(e));
         e.M = xn; e.N = 256; e.mode = LIN_LN;
         e.gamma = params.vec(p + ".ln2.g"); e.beta = params.vec(p + ".ln2.b");
-        e.resid = xf + static_cast<long long>(x0) * 256; e.resid_ld = 256;
-        e.out_f32 = xf + static_cast<long long>(x0) * 256; e.out_f32_ld = 256;
+        if (res_hl()) {
+            // the residual stream lives in the split planes (x = hi + lo carries 22 mantissa bits); the fp32 copy is only
+            // written by the last layer, for the matcher and the fine stage
+            e.res_hi = tok_.x[0].hi + static_cast<long long>(x0) * 256; e.res_lo = tok_.x[0].lo() + static_cast<long long>(x0) * 256; e.res_ld = 256;
+            if (li == 7) { e.out_f32 = xf + static_cast<long long>(x0) * 256; e.out_f32_ld = 256; }
+        } else {
+            e.resid = xf + static_cast<long long>(x0) * 256; e.resid_ld = 256;
+            e.out_f32 = xf + static_cast<long long>(x0) * 256; e.out_f32_ld = 256;
+        }
         e.out_hi = tok_.x[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.x[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
         launch_gemm_counted<256, true, LinEpi>(maps, c3, e, 256, st, "lin");
     }
@@ -546,6 +563,8 @@ void CoarseEngine::match(const float* f0, int h0c, int w0c, const float* f1, int
         c.M = L;
         e.M = L; e.N = S; e.mode = SIM_CONF;
         e.row_lse = tok_.stat[0]; e.col_lse = tok_.stat[1]; e.thr = thr;
+        // conf = 2^(...) > thr: thr > 0 -> exponent > log2(thr); thr == 0 -> any non-zero (subnormal included) result, exponent >= -150
+        e.lthr = thr > 0.f ? log2f(thr) - 0.01f : (thr == 0.f ? -152.f : -INFINITY);
         e.row_best = tok_.best[0]; e.col_best = tok_.best[1]; e.conf_out = conf_out;
         launch_gemm_counted<256, true, SimEpi>(maps, c, e, S, st, "sim");
     }

@@ -3,6 +3,16 @@
 #include "engine_common.h"
 
 namespace dfsfm {
+constexpr int kTlCtas = 148;
+static unsigned long long* g_tl_buf = nullptr;
+static int g_tl_cap = 0, g_tl_used = 0;
+static std::vector<int32_t> g_tl_info;
+unsigned long long* timeline_next_launch(int grid_ctas, int tiles) {
+    if (g_tl_used >= g_tl_cap || grid_ctas > kTlCtas) return nullptr;
+    g_tl_info.push_back(grid_ctas);
+    g_tl_info.push_back(tiles);
+    return g_tl_buf + static_cast<size_t>(g_tl_used++) * kTlCtas * 16;
+}
 
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& s) { g_last_error = s; }
@@ -93,6 +103,34 @@ int64_t dfsfm_launch_count(void) { return dfsfm::launch_counter().load(); }
 
 void dfsfm_set_engine(int version) { dfsfm::set_engine_version(version); }
 int dfsfm_get_engine(void) { return dfsfm::engine_version(); }
+
+int dfsfm_debug_timeline_arm(int max_launches) {
+    using namespace dfsfm;
+    return guard([&] {
+        if (g_tl_buf) { DFSFM_CUDA(cudaFree(g_tl_buf)); g_tl_buf = nullptr; }
+        g_tl_cap = g_tl_used = 0;
+        g_tl_info.clear();
+        if (max_launches > 0) {
+            const size_t bytes = static_cast<size_t>(max_launches) * kTlCtas * 16 * sizeof(unsigned long long);
+            DFSFM_CUDA(cudaMalloc(&g_tl_buf, bytes));
+            DFSFM_CUDA(cudaMemset(g_tl_buf, 0, bytes));
+            g_tl_cap = max_launches;
+        }
+    });
+}
+int dfsfm_debug_timeline_read(uint64_t* stamps, int32_t* info, int max_launches) {
+    using namespace dfsfm;
+    int n = 0;
+    const int rc = guard([&] {
+        DFSFM_CUDA(cudaDeviceSynchronize());
+        n = g_tl_used < max_launches ? g_tl_used : max_launches;
+        if (n > 0) {
+            DFSFM_CUDA(cudaMemcpy(stamps, g_tl_buf, static_cast<size_t>(n) * kTlCtas * 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < 2 * n; ++i) info[i] = g_tl_info[i];
+        }
+    });
+    return rc ? -1 : n;
+}
 
 void dfsfm_profile_enable(int on) {
     dfsfm::g_prof_on = on != 0;

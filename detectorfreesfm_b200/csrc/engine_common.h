@@ -1,5 +1,6 @@
 // Shared by the engine translation units: parameter store, C-ABI error guard, launch counter.
 #pragma once
+#include <type_traits>
 #include <atomic>
 #include <functional>
 #include <map>
@@ -55,8 +56,20 @@ template <int BN, bool kSplit, class Epi>
 inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st,
                                 const char* label = "gemm") {
     LaunchScope ls(label, st);
-    if (engine_version() == 2) launch_gemm2<BN, kSplit, Epi>(maps, core, ep, n_total, st);
-    else launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+    if (engine_version() == 2) {
+        if constexpr (std::is_same<Epi, LinEpi>::value) {
+            // one kernel per epilogue flavour (see LinEpiS)
+            if (ep.mode == LIN_F32_ELU) launch_gemm2<BN, kSplit, LinEpiS<LIN_F32_ELU, 0>>(maps, core, ep, n_total, st);
+            else if (ep.mode == LIN_RELU_HL) launch_gemm2<BN, kSplit, LinEpiS<LIN_RELU_HL, 0>>(maps, core, ep, n_total, st);
+            else if (ep.resid != nullptr) launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 1>>(maps, core, ep, n_total, st);
+            else if (ep.res_hi != nullptr) launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 2>>(maps, core, ep, n_total, st);
+            else launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 0>>(maps, core, ep, n_total, st);
+        } else {
+            launch_gemm2<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+        }
+    } else {
+        launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
+    }
 }
 
 // Fused mlp.0 + ReLU + mlp.2 + norm2 + residual for d_model 128 (mlp_fused.cuh); DFSFM_FUSED_MLP=0 selects the two-GEMM path.

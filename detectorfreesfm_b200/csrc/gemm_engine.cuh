@@ -26,6 +26,14 @@ constexpr int kGemmThreads = 192;   // engine 1: 2 role warps + 4 epilogue warps
 constexpr int kGemm2EpiWarps = 8;  // engine 2: two warps per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int kGemm2Threads = 64 + 32 * kGemm2EpiWarps;
 
+// Engine-2 extras handed to an epilogue warp: its staging buffer (Epi::kEpiStageBytes, null on engine 1), the buffer of the
+// warp that owns the other half of the same rows' columns, and the named barrier the two share.
+struct EpiCtx {
+    uint8_t* stg;
+    uint8_t* stg_partner;
+    int bar_id;
+};
+
 struct TmapPack {
     CUtensorMap a[kMaxAMaps];  // activation planes: dims {C, rows, 2 (hi/lo)}, box {64, 128, 1}
     CUtensorMap b;             // weights: dims {Ktot, Nrows, 2 (hi/lo)}, box {64, BN, 1}
@@ -41,7 +49,16 @@ struct GemmCore {
     int bo_mode;   // tap groups only: 1 = put (address >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
     int8_t tap_map[kMaxTaps];  // which activation map a tap reads
     int tap_shift[kMaxTaps];   // row shift of a tap
+    unsigned long long* tl;    // engine 2, debugging: when set, [CTA][16] globaltimer stamps of this launch (dfsfm_debug_timeline)
 };
+
+__device__ __forceinline__ void tl_stamp(const GemmCore& core, int ev) {
+    if (core.tl != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        core.tl[blockIdx.x * 16 + ev] = t;
+    }
+}
 
 template <int BN, bool kSplit>
 struct GemmCfg {
@@ -158,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, n0, 0, BN,
-                                             static_cast<int>(blockIdx.y), nullptr);
+                                             static_cast<int>(blockIdx.y), EpiCtx{nullptr, nullptr, 0});
         tc_fence_before();
     }
     __syncthreads();
@@ -227,6 +244,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
 
     // Programmatic dependent launch: let the next kernel of the stream start its prologue on SMs we leave idle ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) tl_stamp(core, 0);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -251,8 +269,10 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) tl_stamp(core, 1);
     // ... and wait here, with barriers initialised and TMEM allocated, until the previous kernel's results are visible.
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) tl_stamp(core, 2);
     const int n_iters = (core.num_taps / G) * core.kchunks;
 
     if (warp == 0) {
@@ -302,6 +322,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     const int c = it % core.kchunks;
                     mbar_wait(&full_bar[s], phase);
                     tc_fence_after();
+                    if (it == 0 && tile == cluster_id) tl_stamp(core, 3);
                     const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
                     const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
@@ -326,6 +347,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
                 }
                 umma_commit_2sm(&tmem_full_bar[a]);
+                tl_stamp(core, tile == cluster_id ? 4 : 5);  // MMAs of the first / of the latest tile issued
                 if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
             }
         }
@@ -342,17 +364,24 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
             mbar_wait(&tmem_full_bar[a], aphase);
             tc_fence_after();
+            if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 6 : 8);  // accumulator of the first / latest tile complete
+            EpiCtx ctx;
+            ctx.stg = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + (warp - 2) * Epi::kEpiStageBytes : nullptr;
+            ctx.stg_partner = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + ((warp - 2) ^ 4) * Epi::kEpiStageBytes : nullptr;
+            ctx.bar_id = 1 + quad;
             Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
-                                                 nt * BN, cb, ce, nt * 2 + half,
-                                                 Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + (warp - 2) * Epi::kEpiStageBytes : nullptr);
+                                                 nt * BN, cb, ce, nt * 2 + half, ctx);
             tc_fence_before();
             __syncwarp();
+            if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 7 : 9);  // epilogue of the first / latest tile done (this warp)
             if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
             if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
         }
     }
     tc_fence_before();
+    if (threadIdx.x == 0) tl_stamp(core, 10);
     cluster_sync_all();
+    if (threadIdx.x == 0) tl_stamp(core, 11);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
@@ -429,7 +458,7 @@ struct ConvEpi {
     static constexpr bool kSeparateCorr = true;
     static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, uint8_t* stg) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, const EpiCtx& ctx) {
         const int row = row0 + lane;
         bool valid = row < p.M;
         int n_img = 0, y = 0, x = 0;
@@ -562,14 +591,18 @@ struct LinEpiParams {
     int elu_cols;
     const float* gamma;  // LIN_LN
     const float* beta;
-    const float* resid;  // LIN_LN: optional fp32 residual x (out = x + LN(acc))
+    const float* resid;  // LIN_LN: optional fp32 residual x (out = x + LN(acc)) ...
     int resid_ld;
+    const __half* res_hi;  // ... or the residual as split-fp16 planes (x = hi + lo; engine 2 only), row pitch res_ld
+    const __half* res_lo;
+    int res_ld;
     float* out_f32;
     int out_f32_ld;
     int out_col0;        // column offset added to n for the fp32 output
     __half* out_hi;
     __half* out_lo;
     int out_ld;
+    int dbg;             // tuning aid (DFSFM_LIN_DBG): 1 no global stores, 2 no residual loads, 4 no LN statistics pass, 8 no column blocks
 };
 
 struct LinEpi {
@@ -578,7 +611,21 @@ struct LinEpi {
     static constexpr int kEpiStageBytes = 4096;  // engine 2: one 32 x 32 fp32 block per epilogue warp
     template <int BN, int kCorr>
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx,
-                                               uint8_t* stg) {
+                                               const EpiCtx& ctx) {
+        if constexpr (kCorr == 0) {  // engine 2 (engine 1 keeps a separate correction accumulator and has no staging buffers)
+            if (p.dbg & 8) return;
+            // generic fallback (the engines launch the LinEpiS specialisations instead, see launch_gemm_counted)
+            if (p.mode == LIN_LN) {
+                if (p.resid != nullptr) run_ln_staged<BN, 1>(p, tmem_warp, row0, lane, n0, cb, ctx);
+                else if (p.res_hi != nullptr) run_ln_staged<BN, 2>(p, tmem_warp, row0, lane, n0, cb, ctx);
+                else run_ln_staged<BN, 0>(p, tmem_warp, row0, lane, n0, cb, ctx);
+            } else if (p.mode == LIN_RELU_HL) {
+                run_plain_staged<LIN_RELU_HL>(p, tmem_warp, row0, lane, n0, cb, ce, ctx);
+            } else {
+                run_plain_staged<LIN_F32_ELU>(p, tmem_warp, row0, lane, n0, cb, ce, ctx);
+            }
+            return;
+        }
         const int row = row0 + lane;
         const bool valid = row < p.M;
         float mean = 0.f, rstd = 0.f;
@@ -597,10 +644,6 @@ struct LinEpi {
             const float md = s1 * inv_n;
             mean = pivot + md;
             rstd = rsqrtf(fmaxf(s2 * inv_n - md * md, 0.f) + 1e-5f);
-        }
-        if (stg != nullptr) {
-            run_staged<kCorr>(p, tmem_warp, row0, lane, n0, cb, ce, mean, rstd, stg);
-            return;
         }
 #pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
@@ -657,77 +700,188 @@ struct LinEpi {
         }
     }
 
-    // Engine-2 path.  A thread owns one accumulator ROW (a TMEM lane), so writing results straight from registers makes every
+    // Engine-2 paths.  A thread owns one accumulator ROW (a TMEM lane), so writing results straight from registers makes every
     // warp-wide store touch 32 different cache lines (one per row): the L1 tag stage then costs 32 cycles per instruction and
     // the short-K linears become epilogue-bound.  Here each 32 x 32 block is transposed through a 4 KB swizzled staging
     // buffer (16-byte chunk index XOR row % 8: conflict-free both ways); afterwards lane l owns columns 4*(l%8)..+3 of rows
     // 4*i + l/8, i = 0..7, so a warp-wide access covers four full 128-byte rows -- residual loads and all stores coalesce.
-    template <int kCorr>
-    static __device__ __forceinline__ void run_staged(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, float mean,
-                                                      float rstd, uint8_t* stg) {
-        const int ch = lane & 7, rsub = lane >> 3;
+    // The epilogue is instruction-issue bound (two warps per scheduler), hence the packed conversions and folded FMAs.
+    struct Blk {  // per-lane geometry of the transposed ("coalesced") domain
+        int ch, rsub;
+    };
+    static __device__ __forceinline__ void stage_rows(uint8_t* stg, int lane, const float* v) {
         uint8_t* st_row = stg + lane * 128;
-        const int sw_w = lane & 7;
+        const int sw = lane & 7;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(st_row + ((q ^ sw) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    static __device__ __forceinline__ float4 unstage(const uint8_t* stg, int rl, int ch) {
+        return *reinterpret_cast<const float4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
+    }
+    static __device__ __forceinline__ void store_out(const Params& p, int r, int col, const float4& w) {
+        if (p.dbg & 1) return;
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(r) * p.out_f32_ld + p.out_col0 + col) = w;
+        if (p.out_hi) {
+            uint2 uh, ul;
+            split_f16x2(w.x, w.y, uh.x, ul.x);
+            split_f16x2(w.z, w.w, uh.y, ul.y);
+            const long long o = static_cast<long long>(r) * p.out_ld + col;
+            *reinterpret_cast<uint2*>(p.out_hi + o) = uh;
+            *reinterpret_cast<uint2*>(p.out_lo + o) = ul;
+        }
+    }
+
+    // LIN_F32_ELU / LIN_RELU_HL: block by block.  Loops stay rolled: the epilogue warps walk this code once per tile, and
+    // straight-line code of tens of KB turns instruction fetch into the bottleneck.
+    template <int kMode>
+    static __device__ __forceinline__ void run_plain_staged(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce,
+                                                            const EpiCtx& ctx) {
+        const int ch = lane & 7, rsub = lane >> 3;
 #pragma unroll 1
         for (int c0 = cb; c0 < ce; c0 += 32) {
             const int nb = n0 + c0;
             if (nb >= p.N) break;  // warp-uniform
             const int col = nb + 4 * ch;
-            float4 res[8];
-            if (p.mode == LIN_LN && p.resid) {  // issue the residual loads before waiting on TMEM
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int r = row0 + 4 * i + rsub;
-                    res[i] = r < p.M ? *reinterpret_cast<const float4*>(p.resid + static_cast<long long>(r) * p.resid_ld + col) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
             float v[32];
-            load_acc32<kCorr>(tmem_warp + c0, v);
-            if (p.mode == LIN_LN) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                *reinterpret_cast<float4*>(st_row + ((q ^ sw_w) << 4)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            load_acc32<0>(tmem_warp + c0, v);
+            stage_rows(ctx.stg, lane, v);
             __syncwarp();
-            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.mode == LIN_LN) {
-                g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
-                b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col));
-            }
-            const bool elu = p.mode == LIN_F32_ELU && nb < p.elu_cols;
-#pragma unroll
+            const bool elu = kMode == LIN_F32_ELU && nb < p.elu_cols;
+#pragma unroll 2
             for (int i = 0; i < 8; ++i) {
                 const int rl = 4 * i + rsub;
                 const int r = row0 + rl;
-                float4 w = *reinterpret_cast<const float4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
+                float4 w = unstage(ctx.stg, rl, ch);
                 if (r >= p.M) continue;
-                if (p.mode == LIN_F32_ELU) {
-                    if (elu) {
-                        w.x = w.x > 0.f ? w.x + 1.f : fast_ex2(w.x * 1.4426950408889634f);  // elu(x) + 1 == exp(x), x <= 0
-                        w.y = w.y > 0.f ? w.y + 1.f : fast_ex2(w.y * 1.4426950408889634f);
-                        w.z = w.z > 0.f ? w.z + 1.f : fast_ex2(w.z * 1.4426950408889634f);
-                        w.w = w.w > 0.f ? w.w + 1.f : fast_ex2(w.w * 1.4426950408889634f);
-                    }
-                } else if (p.mode == LIN_RELU_HL) {
+                if (kMode == LIN_RELU_HL) {
                     w.x = fmaxf(w.x, 0.f); w.y = fmaxf(w.y, 0.f); w.z = fmaxf(w.z, 0.f); w.w = fmaxf(w.w, 0.f);
-                } else {
-                    w.x = w.x * g4.x + b4.x; w.y = w.y * g4.y + b4.y; w.z = w.z * g4.z + b4.z; w.w = w.w * g4.w + b4.w;
-                    if (p.resid) { w.x += res[i].x; w.y += res[i].y; w.z += res[i].z; w.w += res[i].w; }
+                } else if (elu) {
+                    w.x = w.x > 0.f ? w.x + 1.f : fast_ex2(w.x * 1.4426950408889634f);  // elu(x) + 1 == exp(x), x <= 0
+                    w.y = w.y > 0.f ? w.y + 1.f : fast_ex2(w.y * 1.4426950408889634f);
+                    w.z = w.z > 0.f ? w.z + 1.f : fast_ex2(w.z * 1.4426950408889634f);
+                    w.w = w.w > 0.f ? w.w + 1.f : fast_ex2(w.w * 1.4426950408889634f);
                 }
-                if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(r) * p.out_f32_ld + p.out_col0 + col) = w;
-                if (p.out_hi) {
-                    uint2 uh, ul;
-                    __half* hh = reinterpret_cast<__half*>(&uh);
-                    __half* hl = reinterpret_cast<__half*>(&ul);
-                    split_f16(w.x, hh[0], hl[0]); split_f16(w.y, hh[1], hl[1]); split_f16(w.z, hh[2], hl[2]); split_f16(w.w, hh[3], hl[3]);
-                    *reinterpret_cast<uint2*>(p.out_hi + static_cast<long long>(r) * p.out_ld + col) = uh;
-                    *reinterpret_cast<uint2*>(p.out_lo + static_cast<long long>(r) * p.out_ld + col) = ul;
-                }
+                store_out(p, r, col, w);
             }
             __syncwarp();
         }
+    }
+
+    // LIN_LN (BN == N == d_model; this warp owns BN/2 columns of 32 rows, its partner warp the other half).  One TMEM pass: the
+    // half-row stays in registers, the two warps exchange (mean, sum of squared deviations) of their halves through shared
+    // memory, then each normalises, transposes and writes its own columns.  TMEM reads run at 64 B/clk/SM, so reading the
+    // tile once instead of three times (statistics by both warps + output) is worth ~2 us per tile.
+    // residual of row r, 4 columns at col, in the transposed domain: fp32 bits, or {hi.x, hi.y, lo.x, lo.y} of the split planes
+    template <int kRes>
+    static __device__ __forceinline__ uint4 load_resid(const Params& p, int r, int col) {
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (r < p.M) {
+            if (kRes == 1) {
+                q = *reinterpret_cast<const uint4*>(p.resid + static_cast<long long>(r) * p.resid_ld + col);
+            } else if (kRes == 2) {
+                const long long o = static_cast<long long>(r) * p.res_ld + col;
+                const uint2 h = *reinterpret_cast<const uint2*>(p.res_hi + o);
+                const uint2 l = *reinterpret_cast<const uint2*>(p.res_lo + o);
+                q = make_uint4(h.x, h.y, l.x, l.y);
+            }
+        }
+        return q;
+    }
+    // transposed phase of one LN block: rows 4i + rsub, i = 0..7.  q[] holds the residual of four rows: on entry rows 0..3 of this
+    // block; an entry is reloaded as soon as it has been consumed -- with row i + 4 of this block, then with rows 0..3 of the
+    // next block (col_next >= 0) -- so a residual load has four rows' worth of work to hide behind.
+    template <int kRes>  // 0: none, 1: fp32 residual, 2: split-fp16 residual
+    static __device__ __forceinline__ void ln_block_out(const Params& p, const EpiCtx& ctx, int row0, int rsub, int ch, int col, int col_next,
+                                                        uint4 (&q)[4]) {
+        constexpr bool has_res = kRes != 0;
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + col));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta + col));
+#pragma unroll 1
+        for (int g = 0; g < 2; ++g) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rl = 4 * (4 * g + k) + rsub;
+                const int r = row0 + rl;
+                float4 w = unstage(ctx.stg, rl, ch);
+                w.x = fmaf(w.x, g4.x, b4.x); w.y = fmaf(w.y, g4.y, b4.y); w.z = fmaf(w.z, g4.z, b4.z); w.w = fmaf(w.w, g4.w, b4.w);
+                if (has_res) {
+                    const uint4 qc = q[k];
+                    if (g == 0) q[k] = load_resid<kRes>(p, r + 16, col);
+                    else if (col_next >= 0) q[k] = load_resid<kRes>(p, r - 16, col_next);
+                    if (kRes == 1) {
+                        w.x += __uint_as_float(qc.x); w.y += __uint_as_float(qc.y); w.z += __uint_as_float(qc.z); w.w += __uint_as_float(qc.w);
+                    } else {
+                        add_f16x2(w.x, w.y, qc.z); add_f16x2(w.z, w.w, qc.w);
+                        add_f16x2(w.x, w.y, qc.x); add_f16x2(w.z, w.w, qc.y);
+                    }
+                }
+                if (r < p.M) store_out(p, r, col, w);
+            }
+        }
+    }
+    template <int BN, int kRes>
+    static __device__ __forceinline__ void run_ln_staged(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, const EpiCtx& ctx) {
+        constexpr int NB = BN / 64;       // 32-column blocks per warp
+        constexpr int NV = 32 * NB;       // columns per warp
+        constexpr bool has_res = kRes != 0;
+        const int ch = lane & 7, rsub = lane >> 3;
+        float v[NV];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) tmem_ld32(tmem_warp + cb + 32 * b, v + 32 * b);
+        uint4 q[4];
+        if (has_res) {  // residual of the first four rows of block 0: in flight behind the TMEM read and the statistics
+#pragma unroll
+            for (int k = 0; k < 4; ++k) q[k] = load_resid<kRes>(p, row0 + 4 * k + rsub, n0 + cb + 4 * ch);
+        }
+        tmem_ld_wait();
+        float scale = 1.f, shift = 0.f;
+        if (!(p.dbg & 4)) {
+            // half-row statistics about the first element (no cancellation), then Chan's combination of the two halves
+            const float pivot = v[0];
+            float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) { const float d = v[j] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+            const float inv_h = 1.f / static_cast<float>(NV);
+            const float m_own = pivot + s1 * inv_h;
+            const float q_own = fmaxf(s2 - s1 * s1 * inv_h, 0.f);
+            *reinterpret_cast<float2*>(ctx.stg + lane * 8) = make_float2(m_own, q_own);
+            named_bar_sync(ctx.bar_id, 64);
+            const float2 o = *reinterpret_cast<const float2*>(ctx.stg_partner + lane * 8);
+            named_bar_sync(ctx.bar_id, 64);  // the partner has read our slot: the staging buffer may be overwritten
+            const float mean = 0.5f * (m_own + o.x);
+            const float dm = m_own - o.x;
+            const float var = (q_own + o.y + 0.5f * static_cast<float>(NV) * dm * dm) * (1.f / static_cast<float>(BN));
+            scale = rsqrtf(var + 1e-5f);
+            shift = -mean * scale;
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            float* vb = v + 32 * b;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) vb[j] = fmaf(vb[j], scale, shift);
+            stage_rows(ctx.stg, lane, vb);
+            __syncwarp();
+            const int col = n0 + cb + 32 * b + 4 * ch;
+            ln_block_out<kRes>(p, ctx, row0, rsub, ch, col, b + 1 < NB ? col + 32 : -1, q);
+            __syncwarp();
+        }
+    }
+};
+
+// Engine-2 specialisations: one kernel per (mode, residual flavour).  The epilogue warps walk their code once per tile, so the
+// instruction footprint matters (a kernel holding every variant measured 2x slower epilogues than one holding just its own).
+template <int kMode, int kRes>
+struct LinEpiS {
+    using Params = LinEpiParams;
+    static constexpr bool kSeparateCorr = false;
+    static constexpr int kEpiStageBytes = LinEpi::kEpiStageBytes;
+    template <int BN, int kCorr>
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx,
+                                               const EpiCtx& ctx) {
+        static_assert(kCorr == 0, "engine 2 only");
+        if (p.dbg & 8) return;
+        if (kMode == LIN_LN) LinEpi::run_ln_staged<BN, kRes>(p, tmem_warp, row0, lane, n0, cb, ctx);
+        else LinEpi::run_plain_staged<kMode>(p, tmem_warp, row0, lane, n0, cb, ce, ctx);
     }
 };
 
@@ -746,6 +900,7 @@ struct SimEpiParams {
     const float* row_lse;  // SIM_CONF: [M] log2-sum-exp2 of the row
     const float* col_lse;  // SIM_CONF: [N]
     float thr;
+    float lthr;     // SIM_CONF: screening bound, a margin below log2(thr) (-inf when thr < 0: every entry is a candidate)
     unsigned long long* row_best;  // [M]
     unsigned long long* col_best;  // [N]
     float* conf_out;               // optional dense [M][N] (debug / small problems)
@@ -760,7 +915,7 @@ struct SimEpi {
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>
-    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, uint8_t* stg) {
+    static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx, const EpiCtx& ctx) {
         const int row = row0 + lane;
         const bool valid = row < p.M;
         if (p.mode == SIM_STATS) {
@@ -796,6 +951,9 @@ struct SimEpi {
         } else {
             const float a_row = valid ? p.row_lse[row] : 0.f;
             const float c22 = 2.f * p.c2;
+            // screening bound in the log2 domain: conf > thr  =>  2t - lse_row - lse_col > lthr (lthr sits a margin below log2(thr),
+            // so rounding differences between the screening and the exact expression below cannot lose a candidate)
+            const float row_bound = valid ? p.lthr + a_row : INFINITY;
             float best = -1.f;
             int best_j = 0;
 #pragma unroll 1
@@ -806,12 +964,23 @@ struct SimEpi {
                 if (nb >= p.N) continue;
                 // lane j holds the column term of column nb + j; +inf for columns past N makes their confidence 0
                 const float b_col = (nb + lane < p.N) ? __ldg(p.col_lse + nb + lane) : INFINITY;
+                float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    m0 = fmaxf(m0, fmaf(v[j], c22, -__shfl_sync(0xffffffffu, b_col, j)));
+                    m1 = fmaxf(m1, fmaf(v[j + 1], c22, -__shfl_sync(0xffffffffu, b_col, j + 1)));
+                    m2 = fmaxf(m2, fmaf(v[j + 2], c22, -__shfl_sync(0xffffffffu, b_col, j + 2)));
+                    m3 = fmaxf(m3, fmaf(v[j + 3], c22, -__shfl_sync(0xffffffffu, b_col, j + 3)));
+                }
+                const bool cand = (fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) > row_bound && valid) || (p.conf_out != nullptr && valid);
+                if (!__any_sync(0xffffffffu, cand)) continue;  // almost every 32 x 32 block: nothing above the threshold
+#pragma unroll 4
                 for (int j = 0; j < 32; ++j) {
                     const float bj = __shfl_sync(0xffffffffu, b_col, j);
+                    if (!cand) continue;
                     const float conf = ex2_denorm(fmaf(v[j], c22, -a_row) - bj);
-                    if (p.conf_out && valid && nb + j < p.N) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
-                    if (conf > p.thr && valid) {
+                    if (p.conf_out && nb + j < p.N) p.conf_out[static_cast<long long>(row) * p.N + nb + j] = conf;
+                    if (conf > p.thr) {
                         atomicMax(p.col_best + nb + j, pack_best(conf, row));
                         if (conf > best) { best = conf; best_j = nb + j; }
                     }

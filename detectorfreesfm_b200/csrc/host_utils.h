@@ -120,6 +120,19 @@ inline bool pdl_enabled() {
     }
     return v == 1;
 }
+inline int lin_debug_flags() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_LIN_DBG");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+inline void set_debug(LinEpiParams& e) { e.dbg = lin_debug_flags(); }
+template <class T>
+inline void set_debug(T&) {}
+// debugging (common.cu): when a timeline capture is armed, the stamp buffer of the next engine-2 launch, else null
+unsigned long long* timeline_next_launch(int grid_ctas, int tiles);
 // engine v2 (persistent CTA pairs).  maps.b must have been built with box rows BN/2.
 template <int BN, bool kSplit, class Epi, int G = 1>
 inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
@@ -152,7 +165,11 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
     attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, core, ep, tiles, n_tiles));
+    GemmCore core_l = core;
+    core_l.tl = timeline_next_launch(2 * clusters, tiles);
+    typename Epi::Params ep_l = ep;
+    set_debug(ep_l);
+    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, core_l, ep_l, tiles, n_tiles));
 }
 
 // Fill the tap table of a stride-1 k x k convolution on a flat-halo geometry with row pitch Wp.

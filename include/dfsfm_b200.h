@@ -106,6 +106,12 @@ int dfsfm_get_engine(void);
  * report() synchronises the device and writes "label count total_ms" lines. Never on inside a timed region. */
 void dfsfm_profile_enable(int on);
 int dfsfm_profile_report(char* buf, int cap);
+/* In-kernel timeline of the engine-2 GEMM (tuning aid): arm(n) makes each of the next n launches record 16 %globaltimer stamps
+ * per CTA (0 entry, 1 set-up done, 2 dependency wait over, 3 first operands landed, 4/5 MMAs of first/last tile issued,
+ * 6/8 accumulator of first/last tile complete, 7/9 its epilogue done, 10 all roles done, 11 exit); read() synchronises and
+ * copies stamps[launch][148][16] and info[launch][2] = {CTAs, tiles}; returns the number of launches captured. */
+int dfsfm_debug_timeline_arm(int max_launches);
+int dfsfm_debug_timeline_read(uint64_t* stamps, int32_t* info, int max_launches);
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 int64_t dfsfm_launch_count(void);
 
