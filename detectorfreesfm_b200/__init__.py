@@ -5,7 +5,7 @@ Host side = thin Python mirroring the reference's plugin interfaces; device side
 """
 from ._lib import DfsfmError, load_library  # noqa: F401
 
-__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher"]
+__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher", "KeypointMerger", "merge_keypoints"]
 
 
 def __getattr__(name):
@@ -15,4 +15,7 @@ def __getattr__(name):
     if name == "B200MultiviewMatcher":
         from .refine_matcher import B200MultiviewMatcher
         return B200MultiviewMatcher
+    if name in ("KeypointMerger", "merge_keypoints"):
+        from . import postprocess
+        return getattr(postprocess, name)
     raise AttributeError(name)

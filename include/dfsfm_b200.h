@@ -91,6 +91,25 @@ int dfsfm_refine_chunk(dfsfm_refine_t* h, int n_img, const float* const* images_
                        const int32_t* q_img_idx, const int32_t* r_img_idx, const uint8_t* movable, float* query_refined,
                        float* ref_refined, float* std_out, void* stream);
 
+/* ---------------------------------------------------------------------- match -> keypoint -> index post-processing
+ * Replaces the per-image Python of src/coarse_match/coarse_match.py:203-237 (Match2Kpts, keypoint_worker with
+ * agg_groupby_2d = np.unique + np.bincount + sorted, update_matches, transform_keypoints;
+ * src/coarse_match/coarse_match_worker.py:151-270, src/coarse_match/utils/merge_kpts.py:4-44).
+ *   rows_dev        [n_rows][5] fp32: x0, y0, x1, y1, conf of every match, pairs concatenated in matches-dict order
+ *   pair_offset_dev [n_pairs+1] first row of every pair (last entry = n_rows)
+ *   pair_images_dev [n_pairs][2] index (into the image list) of the pair's first / second image
+ * Outputs (device; capacity 2*n_rows key points):
+ *   kpt_xy_dev [K][2] fp32 truncated coordinates, kpt_score_dev [K] fp32 summed confidence, images concatenated in list
+ *   order, inside an image ordered by descending fp64 score then (x, y) -- the reference's keypoint ids;
+ *   image_offset_dev [n_images+1] first key point of every image; match_ids_dev [n_rows][2] int32 keypoint ids (local to
+ *   the image) of the two end points of every match.  *n_keypoints = K.  Synchronises the stream. */
+typedef struct dfsfm_post dfsfm_post_t;
+int dfsfm_post_create(dfsfm_post_t** out, int device);
+void dfsfm_post_destroy(dfsfm_post_t* h);
+int dfsfm_post_merge_keypoints(dfsfm_post_t* h, const float* rows_dev, int64_t n_rows, int n_pairs, const int64_t* pair_offset_dev,
+                               const int32_t* pair_images_dev, int n_images, float* kpt_xy_dev, float* kpt_score_dev,
+                               int32_t* image_offset_dev, int32_t* match_ids_dev, int64_t* n_keypoints, void* stream);
+
 /* -------------------------------------------------------------------------------------------------- test / bench hooks */
 /* Shifted-row GEMM engine on raw split-fp16 operands: out[M][N] fp32 = sum_t A[p+shift_t, :cpad] . W[n, t*cpad : (t+1)*cpad].
  * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */

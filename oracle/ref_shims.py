@@ -223,3 +223,44 @@ def multiview_config(window=15, left_window=7):
         "multiview_matching_train": {**mm, "left_point_movement_window_size": None},
         "multiview_matching_test": {**mm, "left_point_movement_window_size": left_window},
     }
+
+
+def import_postprocess():
+    """-> (Match2Kpts, keypoint_worker, update_matches, transform_keypoints) from src/coarse_match.
+
+    src/__init__.py, the dataset and the model builders are never executed: `src` is a bare namespace and the worker
+    module's unrelated imports (ray, pytorch_lightning, the dataset class, src.utils helpers) are inert stubs.
+    """
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    utils = _mod("src.utils")
+    utils.__path__ = []
+    _mod("src.utils.misc", lower_config=lambda c: c)
+    _mod("src.utils.torch_utils", update_state_dict=lambda *a, **k: None, STATE_DICT_MAPPER={})
+    ds = _mod("src.dataset")
+    ds.__path__ = []
+    _mod("src.dataset.coarse_matching_dataset", CoarseMatchingDataset=object)
+
+    class _Remote:
+        def __call__(self, *a, **k):
+            if len(a) == 1 and callable(a[0]) and not k:
+                return a[0]
+            return lambda f: f
+    try:
+        import ray  # noqa: F401
+    except Exception:
+        _mod("ray", remote=_Remote())
+    try:
+        import pytorch_lightning  # noqa: F401
+    except Exception:
+        _mod("pytorch_lightning", seed_everything=lambda s: None)
+    try:
+        import tqdm  # noqa: F401
+    except Exception:
+        _mod("tqdm", tqdm=lambda x, **k: x)
+    worker = importlib.import_module("src.coarse_match.coarse_match_worker")
+    merge = importlib.import_module("src.coarse_match.utils.merge_kpts")
+    return merge.Match2Kpts, worker.keypoint_worker, worker.update_matches, worker.transform_keypoints

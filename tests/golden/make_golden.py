@@ -5,6 +5,7 @@ Fixtures (small, fp32, torch.save):
   roialign_readme.pt   the reference's own known-answer vector (third_party/RoIAlign.pytorch/README.md:42-96)
   loftr_small.pt       LoFTR coarse_only on a 64x80 pair: conf-matrix digest, match ids, mkpts, mconf, feature digests
   multiview_small.pt   MultiviewMatcher on a 24-track chunk: refined points + std
+  postprocess_small.pt Match2Kpts + keypoint_worker + update_matches + transform_keypoints on synthetic matches of 5 images
 """
 import os
 import sys
@@ -73,7 +74,29 @@ def main():
         gm[name] = {"W": W, "LW": LW, "query_points_refined": data["query_points_refined"],
                     "reference_points_refined": data["reference_points_refined"][-1], "std": data["std"][-1]}
     torch.save(gm, os.path.join(HERE, "multiview_small.pt"))
+    # ---- match -> keypoint -> index post-processing (coarse_match.py:203-237), reference functions themselves
+    torch.save(postprocess_golden(), os.path.join(HERE, "postprocess_small.pt"))
     print("golden fixtures written to", HERE)
+
+
+def reference_postprocess(matches, names, split=" "):
+    """the block of src/coarse_match/coarse_match.py:203-237 with the reference's own functions"""
+    M2K, keypoint_worker, update_matches, transform_keypoints = ref_shims.import_postprocess()
+    all_kpts = M2K(matches, names, name_split=split)
+    keypoints = keypoint_worker(all_kpts[0:len(names)], verbose=False)
+    updated = update_matches(matches, keypoints, merge=False, verbose=False, pair_name_split=split)
+    keypoints = {k: v for k, v in keypoints.items() if isinstance(v, dict)}
+    final_kpts, final_scores = transform_keypoints(keypoints, verbose=False)
+    return final_kpts, final_scores, updated
+
+
+def postprocess_golden():
+    import itertools
+    from oracle import postprocess_oracle as po
+    pairs = [p for p in itertools.combinations(range(5), 2) if 4 not in p]  # image 4 never matched
+    matches, names = po.synth_matches(5, pairs, [0, 40, 150], seed=7)
+    fk, fs, upd = reference_postprocess(matches, names)
+    return {"names": names, "matches": matches, "final_keypoints": fk, "final_scores": fs, "updated_matches": upd}
 
 
 if __name__ == "__main__":

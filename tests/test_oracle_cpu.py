@@ -87,3 +87,19 @@ def test_empty_match_set():
     im0, im1 = util.synth_pair(32, 32, seed=2)
     out = lo.loftr_forward({"image0": im0, "image1": im1}, sd, {"thr": 1.0, "temperature": 0.1})
     assert out["mkpts0_f"].shape == (0, 2) and out["mconf"].shape == (0,)
+
+
+def test_postprocess_oracle_vs_golden():
+    """oracle/postprocess_oracle.py reproduces the reference's own outputs stored in tests/golden/postprocess_small.pt."""
+    import numpy as np
+    from oracle import postprocess_oracle as po
+    g = torch.load(os.path.join(GOLD, "postprocess_small.pt"), weights_only=False)
+    fk, fs, upd = po.merge_keypoints(g["matches"], g["names"], " ")
+    n_kp = 0
+    for name in g["names"]:
+        assert np.array_equal(fk[name], g["final_keypoints"][name]) and fk[name].dtype == g["final_keypoints"][name].dtype
+        assert np.array_equal(fs[name], g["final_scores"][name]) and fs[name].dtype == np.float32
+        n_kp += fk[name].shape[0]
+    for k, v in g["updated_matches"].items():
+        assert np.array_equal(upd[k], v) and upd[k].shape == v.shape
+    assert n_kp > 100 and g["final_keypoints"][g["names"][4]].shape == (0, 2)

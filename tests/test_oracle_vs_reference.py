@@ -60,3 +60,24 @@ def test_c_roialign_matches_reference_cpp():
     crops = torch.zeros(1)
     ext.forward(image, nb.contiguous(), bi, 0.0, 35, 35, crops)
     assert torch.equal(build_native.roialign_forward(image, nb, bi, 35, 35), crops)
+
+
+def test_postprocess_oracle_matches_reference():
+    """Match2Kpts / keypoint_worker / update_matches / transform_keypoints themselves vs oracle/postprocess_oracle.py: equal
+    arrays, dtypes and shapes, including pairs without matches and an image that never appears."""
+    import itertools
+    import numpy as np
+    from oracle import postprocess_oracle as po
+    from tests.golden.make_golden import reference_postprocess
+    for seed, (n, m) in enumerate([(4, 50), (6, 300), (5, [0, 10, 200]), (3, 1)]):
+        pairs = list(itertools.combinations(range(n), 2))
+        if seed == 2:
+            pairs = [p for p in pairs if 4 not in p]
+        matches, names = po.synth_matches(n, pairs, m, seed=seed)
+        ref = reference_postprocess(matches, names)
+        ora = po.merge_keypoints(matches, names, " ")
+        for name in names:
+            for a, b in ((ref[0][name], ora[0][name]), (ref[1][name], ora[1][name])):
+                assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
+        for k in matches:
+            assert ref[2][k].dtype == ora[2][k].dtype and ref[2][k].shape == ora[2][k].shape and np.array_equal(ref[2][k], ora[2][k])
