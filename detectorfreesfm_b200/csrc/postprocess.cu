@@ -335,7 +335,7 @@ public:
         { LaunchScope ls("post_keys", st);
           obs_key_kernel<<<static_cast<unsigned>((N + tb - 1) / tb), tb, 0, st>>>(rows, T, pair_off_dev, pair_img_dev, m, keys[0], vals[0]); }
         int cur = 0;
-        cur = radix_sort(keys, vals, cur, N, 0, m.xb + m.yb + ib, hist, bsums, st);
+        cur = radix_sort(keys, vals, cur, N, 0, m.xb + m.yb + ib, hist, bsums, st, "post_scatter");
         { LaunchScope ls("post_flag", st);
           head_flag_kernel<<<static_cast<unsigned>((N + tb - 1) / tb), tb, 0, st>>>(keys[cur], N, flag); }
         int* total = range;  // reuse the small buffer
@@ -353,11 +353,11 @@ public:
         // second sort: keys[oth]/vals[oth] hold (~score bits, u) in (image, x, y) order; ping-pong partner is a fresh pair
         unsigned long long* k2[2] = {keys[oth], static_cast<unsigned long long*>(k2_.get(static_cast<size_t>(K) * 8))};
         unsigned int* v2[2] = {vals[oth], static_cast<unsigned int*>(v2_.get(static_cast<size_t>(K) * 4))};
-        int c2 = radix_sort(k2, v2, 0, K, 0, 64, hist, bsums, st);
+        int c2 = radix_sort(k2, v2, 0, K, 0, 64, hist, bsums, st, "post_scatter_rank");
         if (ib > 0) {
             { LaunchScope ls("post_imgkey", st);
               image_key_kernel<<<(K + tb - 1) / tb, tb, 0, st>>>(v2[c2], ukey, K, m.xb + m.yb, k2[c2]); }
-            c2 = radix_sort(k2, v2, c2, K, 0, ib, hist, bsums, st);
+            c2 = radix_sort(k2, v2, c2, K, 0, ib, hist, bsums, st, "post_scatter_rank");
         }
         { LaunchScope ls("post_emit", st);
           emit_kernel<<<(K + tb - 1) / tb, tb, 0, st>>>(v2[c2], ukey, usum, K, m, kpt_xy, kpt_score, img_off, rank_of_u); }
@@ -385,14 +385,14 @@ private:
     }
     // LSD passes over key bits [bit_lo, bit_hi); returns the index of the buffer pair holding the result
     int radix_sort(unsigned long long* keys[2], unsigned int* vals[2], int cur, long long n, int bit_lo, int bit_hi, int* hist, int* bsums,
-                   cudaStream_t st) {
+                   cudaStream_t st, const char* scatter_label) {
         const int nseg = static_cast<int>((n + kSeg - 1) / kSeg);
         const int nblk = (nseg + 7) / 8;
         for (int shift = bit_lo; shift < bit_hi; shift += 8) {
             { LaunchScope ls("post_hist", st);
               rs_hist_kernel<<<nblk, 256, 0, st>>>(keys[cur], n, shift, nseg, hist); }
             exclusive_scan(hist, hist, static_cast<long long>(nseg) * 256, bsums, nullptr, st);
-            { LaunchScope ls(n > (1 << 20) ? "post_scatter" : "post_scatter_small", st);
+            { LaunchScope ls(scatter_label, st);
               rs_scatter_kernel<<<nblk, 256, 0, st>>>(keys[cur], vals[cur], n, shift, nseg, hist, keys[cur ^ 1], vals[cur ^ 1]); }
             cur ^= 1;
         }

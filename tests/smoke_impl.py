@@ -37,3 +37,17 @@ def run():
     dr = (d["reference_points_refined"][-1].cpu() - refm["reference_points_refined"])[mask].abs().max().item()
     assert dq < 1e-3 and dr < 0.1, (dq, dr)
     print(f"[smoke] HP-2 refinement chunk: max |d query| = {dq:.2e} px, max |d refined| = {dr:.2e} px")
+
+    # post-processing: 4 images, 6 pairs, bit-exact vs the numpy oracle
+    import itertools
+    import numpy as np
+    from detectorfreesfm_b200 import merge_keypoints
+    from oracle import postprocess_oracle as po
+    matches, names = po.synth_matches(4, list(itertools.combinations(range(4), 2)), 120, seed=2)
+    ref_k, ref_s, ref_m = po.merge_keypoints(matches, names, " ")
+    out_k, out_s, out_m = merge_keypoints(matches, names, " ")
+    for n in names:
+        assert np.array_equal(out_k[n], ref_k[n]) and np.array_equal(out_s[n], ref_s[n])
+    for k in matches:
+        assert np.array_equal(out_m[k], ref_m[k])
+    print(f"[smoke] post-processing: {sum(v.shape[0] for v in out_k.values())} key points from {sum(v.shape[0] for v in matches.values())} matches, bit-exact")
