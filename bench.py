@@ -307,60 +307,63 @@ def main():
     # ------------------------------------------------------------------ match -> keypoint -> index post-processing
     post = None
     if not args.skip_post:
-        from detectorfreesfm_b200 import KeypointMerger
-        from oracle import postprocess_oracle as po
-        n_img, m_pair = 64, 2000
-        pairs = list(itertools.combinations(range(n_img), 2))
-        pm, names = po.synth_matches(n_img, pairs, m_pair, seed=5 + rank, dup=0.25)
-        merger = KeypointMerger(dev)
-        rows_host = torch.from_numpy(np.concatenate(list(pm.values()), 0)).pin_memory()
-        rows_dev = rows_host.to(dev)
-        counts = np.array([v.shape[0] for v in pm.values()], dtype=np.int64)
-        pair_off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(dev)
-        index = {n: i for i, n in enumerate(names)}
-        pair_img = torch.tensor([[index[k.split(" ")[0]], index[k.split(" ")[1]]] for k in pm], dtype=torch.int32, device=dev)
-        n_obs = 2 * int(rows_dev.shape[0])
+        try:
+            from detectorfreesfm_b200 import KeypointMerger
+            from oracle import postprocess_oracle as po
+            n_img, m_pair = 64, 2000
+            pairs = list(itertools.combinations(range(n_img), 2))
+            pm, names = po.synth_matches(n_img, pairs, m_pair, seed=5 + rank, dup=0.25)
+            merger = KeypointMerger(dev)
+            rows_host = torch.from_numpy(np.concatenate(list(pm.values()), 0)).pin_memory()
+            rows_dev = rows_host.to(dev)
+            counts = np.array([v.shape[0] for v in pm.values()], dtype=np.int64)
+            pair_off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).to(dev)
+            index = {n: i for i, n in enumerate(names)}
+            pair_img = torch.tensor([[index[k.split(" ")[0]], index[k.split(" ")[1]]] for k in pm], dtype=torch.int32, device=dev)
+            n_obs = 2 * int(rows_dev.shape[0])
 
-        def post_resident():
-            return merger.merge(rows_dev, pair_off, pair_img, n_img)
+            def post_resident():
+                return merger.merge(rows_dev, pair_off, pair_img, n_img)
 
-        def post_e2e():
-            out = merger.merge(rows_host.to(dev, non_blocking=True), pair_off, pair_img, n_img)
-            return [o.cpu() for o in out]
+            def post_e2e():
+                out = merger.merge(rows_host.to(dev, non_blocking=True), pair_off, pair_img, n_img)
+                return [o.cpu() for o in out]
 
-        for _ in range(2):
-            post_resident()
-        k3 = max(2, min(K, 3))
-        ms3 = timed(post_resident, k3, False)
-        ms3_e2e = timed(post_e2e, k3, False)
-        lib.dfsfm_profile_enable(1)
-        kp = post_resident()
-        prof3 = profile_report(lib)
-        lib.dfsfm_profile_enable(0)
-        sc_cnt, sc_ms = prof3.get("post_scatter", (0, 0.0))
-        rec_bytes = 24.0 * n_obs   # one pass streams every 12-byte (key, value) record in and out once
-        post = {"metric": "match end points/s merged into key points", "value": n_obs * k3 * world / (ms3 * 1e-3), "unit": "observations/s",
-                "ms_per_call": ms3 / k3, "observations": n_obs, "pairs": len(pairs), "images": n_img, "keypoints": int(kp[0].shape[0]),
-                "e2e": {"value": n_obs * k3 * world / (ms3_e2e * 1e-3), "unit": "observations/s", "h2d_bytes_per_step": rows_host.numel() * 4,
-                        "d2h_bytes_per_step": int(kp[0].numel() * 4 + kp[1].numel() * 4 + kp[3].numel() * 4)},
-                "roofline": {"bound": "hbm", "kernel": "rs_scatter_kernel (one 8-bit LSD radix pass over the observation records)",
-                             "achieved": rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 if sc_cnt else None, "peak": peaks.get("hbm"), "unit": "GB/s",
-                             "frac": (rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 / peaks["hbm"]) if sc_cnt and peaks.get("hbm") else None,
-                             "traffic": None, "launches": sc_cnt,
-                             "kernel_ms_per_call": {k: round(v[1], 3) for k, v in sorted(prof3.items())}}}
-        if rank == 0 and world == 1 and not args.skip_cpu:
-            sub_pairs = list(itertools.combinations(range(12), 2))
-            sub, sub_names = po.synth_matches(12, sub_pairs, m_pair, seed=5, dup=0.25)
-            t0 = time.perf_counter()
-            reps = 0
-            while reps < 3 and time.perf_counter() - t0 < 15:
-                po.merge_keypoints(sub, sub_names, " ")
-                reps += 1
-            dt = time.perf_counter() - t0
-            post["cpu_baseline"] = {"value": 2 * len(sub_pairs) * m_pair * reps / dt, "unit": "observations/s", "cores": 1, "kind": "port",
-                                    "sample": f"{reps} x 12 images / {len(sub_pairs)} pairs x {m_pair} matches, oracle/postprocess_oracle.py "
-                                              "(numpy np.unique/bincount/argsort restatement, pinned to the reference functions; the "
-                                              "reference itself adds per-match Python dict look-ups)"}
+            for _ in range(2):
+                post_resident()
+            k3 = max(2, min(K, 3))
+            ms3 = timed(post_resident, k3, False)
+            ms3_e2e = timed(post_e2e, k3, False)
+            lib.dfsfm_profile_enable(1)
+            kp = post_resident()
+            prof3 = profile_report(lib)
+            lib.dfsfm_profile_enable(0)
+            sc_cnt, sc_ms = prof3.get("post_scatter", (0, 0.0))
+            rec_bytes = 24.0 * n_obs   # one pass streams every 12-byte (key, value) record in and out once
+            post = {"metric": "match end points/s merged into key points", "value": n_obs * k3 * world / (ms3 * 1e-3), "unit": "observations/s",
+                    "ms_per_call": ms3 / k3, "observations": n_obs, "pairs": len(pairs), "images": n_img, "keypoints": int(kp[0].shape[0]),
+                    "e2e": {"value": n_obs * k3 * world / (ms3_e2e * 1e-3), "unit": "observations/s", "h2d_bytes_per_step": rows_host.numel() * 4,
+                            "d2h_bytes_per_step": int(kp[0].numel() * 4 + kp[1].numel() * 4 + kp[3].numel() * 4)},
+                    "roofline": {"bound": "hbm", "kernel": "rs_scatter_kernel (one 8-bit LSD radix pass over the observation records)",
+                                 "achieved": rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 if sc_cnt else None, "peak": peaks.get("hbm"), "unit": "GB/s",
+                                 "frac": (rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 / peaks["hbm"]) if sc_cnt and peaks.get("hbm") else None,
+                                 "traffic": None, "launches": sc_cnt,
+                                 "kernel_ms_per_call": {k: round(v[1], 3) for k, v in sorted(prof3.items())}}}
+            if rank == 0 and world == 1 and not args.skip_cpu:
+                sub_pairs = list(itertools.combinations(range(12), 2))
+                sub, sub_names = po.synth_matches(12, sub_pairs, m_pair, seed=5, dup=0.25)
+                t0 = time.perf_counter()
+                reps = 0
+                while reps < 3 and time.perf_counter() - t0 < 15:
+                    po.merge_keypoints(sub, sub_names, " ")
+                    reps += 1
+                dt = time.perf_counter() - t0
+                post["cpu_baseline"] = {"value": 2 * len(sub_pairs) * m_pair * reps / dt, "unit": "observations/s", "cores": 1, "kind": "port",
+                                        "sample": f"{reps} x 12 images / {len(sub_pairs)} pairs x {m_pair} matches, oracle/postprocess_oracle.py "
+                                                  "(numpy np.unique/bincount/argsort restatement, pinned to the reference functions; the "
+                                                  "reference itself adds per-match Python dict look-ups)"}
+        except Exception as e:  # the secondary leg must never take the headline line down with it
+            post = {"error": repr(e)}
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
