@@ -5,7 +5,7 @@ Host side = thin Python mirroring the reference's plugin interfaces; device side
 """
 from ._lib import DfsfmError, load_library  # noqa: F401
 
-__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher", "KeypointMerger", "merge_keypoints"]
+__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher", "KeypointMerger", "merge_keypoints", "GpuImageReader", "B200CoarseMatchingDataset"]
 
 
 def __getattr__(name):
@@ -18,4 +18,7 @@ def __getattr__(name):
     if name in ("KeypointMerger", "merge_keypoints"):
         from . import postprocess
         return getattr(postprocess, name)
+    if name in ("GpuImageReader", "B200CoarseMatchingDataset"):
+        from . import image_pipeline
+        return getattr(image_pipeline, name)
     raise AttributeError(name)

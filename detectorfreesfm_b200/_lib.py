@@ -25,6 +25,8 @@ PROTOTYPES = {
     "dfsfm_post_destroy": (None, [c_void_p]),
     "dfsfm_post_merge_keypoints": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                            ctypes.POINTER(c_int64), c_void_p]),
+    "dfsfm_resize_lanczos_gray": (c_int, [c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p]),
     "dfsfm_debug_timeline_arm": (c_int, [c_int]),
     "dfsfm_debug_timeline_read": (c_int, [c_void_p, c_void_p, c_int]),
     "dfsfm_coarse_create": (c_int, [ctypes.POINTER(c_void_p), c_int]),

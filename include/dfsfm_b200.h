@@ -110,6 +110,17 @@ int dfsfm_post_merge_keypoints(dfsfm_post_t* h, const float* rows_dev, int64_t n
                                const int32_t* pair_images_dev, int n_images, float* kpt_xy_dev, float* kpt_score_dev,
                                int32_t* image_offset_dev, int32_t* match_ids_dev, int64_t* n_keypoints, void* stream);
 
+/* ---------------------------------------------------------------------- host image pipeline, device part
+ * The PIL-LANCZOS resize + /255 of read_grayscale (src/dataset/utils.py:137-148, resize_image :161-177 with interp
+ * "pil_LANCZOS"; grayscale2tensor :56-57).  img_dev: uint8 [h][ld] grayscale (cv2.IMREAD_GRAYSCALE).  The fixed-point tables
+ * are Pillow's (Resample.c precompute_coeffs + normalize_coeffs_8bpc; built on the host by image_pipeline.lanczos_coeffs):
+ * bounds [out][2] = (first input index, tap count), coef [out][ksize] int32 with 22 fractional bits; pass null tables for a
+ * dimension that keeps its size (Pillow skips that pass).  tmp_dev: h*out_w bytes when both passes run.
+ * out_dev: fp32 [out_h][out_w] = resized uint8 / 255 -- bit-identical to the reference's tensor. */
+int dfsfm_resize_lanczos_gray(const uint8_t* img_dev, int h, int w, int64_t ld, const int32_t* xbounds_dev, const int32_t* xcoef_dev, int xksize,
+                              const int32_t* ybounds_dev, const int32_t* ycoef_dev, int yksize, int out_h, int out_w, uint8_t* tmp_dev,
+                              float* out_dev, void* stream);
+
 /* -------------------------------------------------------------------------------------------------- test / bench hooks */
 /* Shifted-row GEMM engine on raw split-fp16 operands: out[M][N] fp32 = sum_t A[p+shift_t, :cpad] . W[n, t*cpad : (t+1)*cpad].
  * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */

@@ -264,3 +264,22 @@ def import_postprocess():
     worker = importlib.import_module("src.coarse_match.coarse_match_worker")
     merge = importlib.import_module("src.coarse_match.utils.merge_kpts")
     return merge.Match2Kpts, worker.keypoint_worker, worker.update_matches, worker.transform_keypoints
+
+
+def import_image_utils():
+    """-> the reference's src/dataset/utils.py module (read_grayscale, process_resize, resize_image).
+
+    Its unrelated imports that this image lacks (h5py, albumentations) are inert stubs; cv2 and PIL are real."""
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    ds = _mod("src.dataset")
+    ds.__path__ = [os.path.join(REF, "src", "dataset")]
+    for name in ("h5py", "albumentations"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            _mod(name)
+    return importlib.import_module("src.dataset.utils")

@@ -6,6 +6,7 @@ Fixtures (small, fp32, torch.save):
   loftr_small.pt       LoFTR coarse_only on a 64x80 pair: conf-matrix digest, match ids, mkpts, mconf, feature digests
   multiview_small.pt   MultiviewMatcher on a 24-track chunk: refined points + std
   postprocess_small.pt Match2Kpts + keypoint_worker + update_matches + transform_keypoints on synthetic matches of 5 images
+  image_small.pt       read_grayscale (cv2 decode of a PNG written here, PIL-LANCZOS resize, /255) on three synthetic images
 """
 import os
 import sys
@@ -76,7 +77,29 @@ def main():
     torch.save(gm, os.path.join(HERE, "multiview_small.pt"))
     # ---- match -> keypoint -> index post-processing (coarse_match.py:203-237), reference functions themselves
     torch.save(postprocess_golden(), os.path.join(HERE, "postprocess_small.pt"))
+    torch.save(image_golden(), os.path.join(HERE, "image_small.pt"))
     print("golden fixtures written to", HERE)
+
+
+def reference_read_grayscale(image_u8, resize, df, tmpdir):
+    """the reference's read_grayscale on a losslessly written PNG of image_u8 -> (tensor, scales, original_hw)"""
+    import cv2
+    utils = ref_shims.import_image_utils()
+    path = os.path.join(tmpdir, "img.png")
+    assert cv2.imwrite(path, image_u8)
+    return utils.read_grayscale(path, resize, df=df, ret_scales=True)
+
+
+def image_golden():
+    import tempfile
+    from oracle import image_oracle as io
+    out = []
+    with tempfile.TemporaryDirectory() as d:
+        for seed, (h, w, resize, df) in enumerate([(150, 200, (96,), 8), (97, 61, (128,), 8), (64, 80, None, None)]):
+            img = io.synth_photo(h, w, seed)
+            t, scales, hw = reference_read_grayscale(img, resize, df, d)
+            out.append({"image": torch.from_numpy(img), "resize": resize, "df": df, "tensor": t, "scales": scales, "original_hw": hw})
+    return out
 
 
 def reference_postprocess(matches, names, split=" "):

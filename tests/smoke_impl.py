@@ -51,3 +51,13 @@ def run():
     for k in matches:
         assert np.array_equal(out_m[k], ref_m[k])
     print(f"[smoke] post-processing: {sum(v.shape[0] for v in out_k.values())} key points from {sum(v.shape[0] for v in matches.values())} matches, bit-exact")
+
+    # image pipeline: GPU Lanczos resize + /255 vs PIL (the reference's resize), bit-exact
+    from PIL import Image
+    from detectorfreesfm_b200 import GpuImageReader
+    from oracle import image_oracle as imo
+    photo = imo.synth_photo(300, 400, 1)
+    ref_img = np.asarray(Image.fromarray(photo).resize((160, 120), resample=Image.LANCZOS)).astype("float32") / 255.
+    out_img = GpuImageReader().resize_gray(photo, (160, 120)).cpu().numpy()
+    assert np.array_equal(out_img, ref_img)
+    print("[smoke] image pipeline: 300x400 -> 120x160 PIL-LANCZOS parity, bit-exact")

@@ -103,3 +103,32 @@ def test_postprocess_oracle_vs_golden():
     for k, v in g["updated_matches"].items():
         assert np.array_equal(upd[k], v) and upd[k].shape == v.shape
     assert n_kp > 100 and g["final_keypoints"][g["names"][4]].shape == (0, 2)
+
+
+def test_image_oracle_vs_golden_and_pillow_restatement():
+    """read_grayscale outputs stored from the reference; the numpy restatement of Pillow's 8-bit resampler equals PIL itself."""
+    import numpy as np
+    from PIL import Image
+    from oracle import image_oracle as io
+    for g in torch.load(os.path.join(GOLD, "image_small.pt"), weights_only=False):
+        t, s, hw = io.read_grayscale_from_array(g["image"].numpy(), g["resize"], df=g["df"])
+        assert torch.equal(t, g["tensor"]) and torch.equal(s, g["scales"]) and torch.equal(hw, g["original_hw"])
+    for (H, W, oh, ow) in [(120, 160, 90, 120), (100, 37, 64, 24), (33, 50, 99, 120), (64, 64, 64, 32), (17, 17, 17, 17), (5, 7, 1, 1),
+                           (700, 900, 208, 264)]:
+        img = io.synth_photo(H, W, seed=H + W)
+        ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.LANCZOS))
+        assert np.array_equal(ref, io.resample_8bpc(img, ow, oh)), (H, W, oh, ow)
+
+
+def test_host_lanczos_tables_equal_oracle_tables():
+    """detectorfreesfm_b200.image_pipeline builds the same fixed-point tables (and the same sizes) as the oracle restatement."""
+    import numpy as np
+    from detectorfreesfm_b200 import image_pipeline as ip
+    from oracle import image_oracle as io
+    for a, b in [(640, 480), (480, 640), (4000, 832), (37, 24), (50, 120), (7, 1), (832, 832)]:
+        b1, k1 = io.coeffs(a, b)
+        b2, k2 = ip.lanczos_coeffs(a, b)
+        assert np.array_equal(b1, b2) and np.array_equal(k1, k2)
+    for args in [(800, 600, (512,), 8, False), (600, 800, (1200,), 8, False), (640, 480, (-1,), 8, False), (640, 480, (320, 200), None, False),
+                 (300, 200, (1200,), 8, True)]:
+        assert ip.process_resize(*args) == io.process_resize(*args)

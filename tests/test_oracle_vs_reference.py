@@ -81,3 +81,14 @@ def test_postprocess_oracle_matches_reference():
                 assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b)
         for k in matches:
             assert ref[2][k].dtype == ora[2][k].dtype and ref[2][k].shape == ora[2][k].shape and np.array_equal(ref[2][k], ora[2][k])
+
+
+def test_image_oracle_matches_reference_read_grayscale(tmp_path):
+    """the reference's read_grayscale (cv2 decode of a PNG, PIL LANCZOS, /255) vs oracle/image_oracle.py: equal tensors, scales."""
+    from oracle import image_oracle as io
+    from tests.golden.make_golden import reference_read_grayscale
+    for seed, (h, w, resize, df) in enumerate([(150, 200, (96,), 8), (97, 61, (128,), 8), (64, 80, None, None), (300, 200, (64, 48), None)]):
+        img = io.synth_photo(h, w, seed)
+        t, scales, hw = reference_read_grayscale(img, resize, df, str(tmp_path))
+        to, so, ho = io.read_grayscale_from_array(img, resize, df=df)
+        assert t.dtype == to.dtype and torch.equal(t, to) and torch.equal(scales, so) and torch.equal(hw, ho)
