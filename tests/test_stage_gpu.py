@@ -1,0 +1,65 @@
+"""Row a1 + 8(f) rows 1 and 3 together: decoded images -> GPU resize -> B200LoFTR -> GPU post-processing vs the three oracles
+chained on the CPU."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_coarse_matching_stage_matches_oracle_chain(tmp_path):
+    import cv2
+    from detectorfreesfm_b200 import B200LoFTR
+    from detectorfreesfm_b200.coarse_stage import coarse_matching_stage, match_worker
+    from oracle import image_oracle as io
+    from oracle import loftr_oracle as lo
+    from oracle import postprocess_oracle as po
+    from oracle import weights
+    from tests import util
+
+    # three views of the same synthetic texture, written as PNGs larger than the matching resolution
+    base = (util.synth_image(180, 240, 21)[0, 0].numpy() * 255).astype(np.uint8)
+    paths, imgs = [], []
+    for i in range(3):
+        img = np.roll(base, (4 * i, 7 * i), (0, 1))
+        p = str(tmp_path / f"view{i}.png")
+        assert cv2.imwrite(p, img)
+        paths.append(p)
+        imgs.append(img)
+    pairs = [f"{paths[a]} {paths[b]}" for a, b in ((0, 1), (0, 2), (1, 2))]
+    thr, temp = 0.0, 0.01
+    cfgs = {"data": {"img_resize": 128, "df": 8, "pad_to": None, "img_preload": False, "img_type": "grayscale"},
+            "matcher": {"model": {"type": "coarse_only"}, "round_matches_ratio": None, "pair_name_split": " "}}
+    sd = weights.loftr_state_dict(0)
+    matcher = B200LoFTR(util.loftr_config(thr=thr, temperature=temp)).cuda().eval()
+    matcher.load_state_dict(sd)
+    fk, fs, upd, raw = coarse_matching_stage(paths, pairs, cfgs, matcher)
+
+    # oracle chain
+    tens = [io.read_grayscale_from_array(im, (128,), df=8) for im in imgs]
+    ref_matches = {}
+    for key, (a, b) in zip(pairs, ((0, 1), (0, 2), (1, 2))):
+        out = lo.loftr_forward({"image0": tens[a][0][None], "image1": tens[b][0][None], "scale0": tens[a][1][None], "scale1": tens[b][1][None]},
+                               sd, {"thr": thr, "temperature": temp})
+        ref_matches[key] = torch.cat([out["mkpts0_f"], out["mkpts1_f"], out["mconf"][:, None]], -1).numpy()
+    n_total = 0
+    for key in pairs:
+        got, ref = raw[key].cpu().numpy(), ref_matches[key]
+        assert got.shape == ref.shape and got.shape[0] > 0
+        assert np.array_equal(got[:, :4], ref[:, :4])                        # same match set, same coordinates
+        assert np.abs(got[:, 4] - ref[:, 4]).max() < 1e-3                    # confidences within the HP-1 tolerance
+        n_total += got.shape[0]
+    rk, rs, ru = po.merge_keypoints(ref_matches, paths, " ")
+    for p in paths:
+        assert fk[p].shape == rk[p].shape
+        # ranking may swap key points whose summed scores differ by less than the confidence tolerance: compare as sets ...
+        assert set(map(tuple, fk[p].tolist())) == set(map(tuple, rk[p].tolist()))
+        assert np.abs(np.sort(fs[p]) - np.sort(rs[p])).max() < 3e-3
+    for key in pairs:                                                          # ... and the indices through the coordinates
+        p0, p1 = key.split(" ")
+        got = raw[key].cpu().numpy()
+        assert np.array_equal(fk[p0][upd[key][:, 0]], np.trunc(got[:, 0:2])) and np.array_equal(fk[p1][upd[key][:, 1]], np.trunc(got[:, 2:4]))
+    # numpy outputs of the worker mirror (the reference's return type) carry the same values
+    m_np = match_worker([0, 1, 2], paths, pairs, cfgs, matcher)
+    assert all(isinstance(v, np.ndarray) and v.dtype == np.float32 and np.array_equal(v, raw[k].cpu().numpy()) for k, v in m_np.items())
+    assert n_total > 10
