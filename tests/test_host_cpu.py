@@ -36,6 +36,17 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     rc = _lib.load_library().dfsfm_coarse_create(ctypes.byref(h), 0)
     assert rc != 0 and _lib.load_library().dfsfm_last_error()
+    # the section-8(f) rows have no CPU path either
+    import numpy as np
+    from detectorfreesfm_b200 import GpuImageReader, KeypointMerger, merge_keypoints
+    with pytest.raises(DfsfmError):
+        KeypointMerger()
+    with pytest.raises(DfsfmError):
+        merge_keypoints({"a b": np.zeros((1, 5), dtype=np.float32)}, ["a", "b"], " ")
+    with pytest.raises(DfsfmError):
+        GpuImageReader()
+    rc = _lib.load_library().dfsfm_post_create(ctypes.byref(h), 0)
+    assert rc != 0
 
 
 def test_unsupported_configs_are_rejected():
@@ -129,3 +140,95 @@ def test_shard_covers_every_unit_once():
         assert seen == list(range(n))
         sizes = [len(shard(n, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def _oracle_flat_merge(rows5, pair_off, pair_img, n_images):
+    """Stand-in for KeypointMerger.merge on the CPU (tests only): the numpy oracle behind the same flat-array signature."""
+    import numpy as np
+    from oracle import postprocess_oracle as po
+    rows = rows5.cpu().numpy()
+    names = [f"i{i}" for i in range(n_images)]
+    matches = {}
+    for p in range(len(pair_img)):
+        matches[f"{names[pair_img[p][0]]} {names[pair_img[p][1]]} #{p}"] = rows[pair_off[p]:pair_off[p + 1]]
+    # one oracle call per image: its observations in pseudo-pair order form the first image of a two-image helper problem
+    per_image = {n: [] for n in names}
+    for key, v in matches.items():
+        a, b, _ = key.split(" ")
+        per_image[a].append((key, 0))
+        per_image[b].append((key, 1))
+    ids = {k: np.zeros((v.shape[0], 2), dtype=np.int32) for k, v in matches.items()}
+    xy, sc, off = [], [], [0]
+    for n in names:
+        parts = [matches[k][:, [2 * s, 2 * s + 1, 4]] for k, s in per_image[n]]
+        kp = np.concatenate(parts, 0) if parts else np.empty((0, 3), dtype=np.float32)
+        if kp.shape[0]:
+            single = po.merge_keypoints({"a b": np.concatenate([kp[:, :2], np.zeros_like(kp[:, :2]), kp[:, 2:3]], 1).astype(np.float32)}, ["a", "b"], " ")
+            # image "a" of the helper call carries exactly this image's observations (image "b" is a sink)
+            k_a, s_a, m_a = single[0]["a"], single[1]["a"], single[2]["a b"][:, 0]
+            pos = 0
+            for k, s in per_image[n]:
+                m = matches[k].shape[0]
+                ids[k][:, s] = m_a[pos:pos + m]
+                pos += m
+        else:
+            k_a, s_a = np.empty((0, 2), dtype=np.float32), np.empty((0,), dtype=np.float32)
+        xy.append(k_a.astype(np.float32).reshape(-1, 2))
+        sc.append(s_a.astype(np.float32))
+        off.append(off[-1] + k_a.shape[0])
+    all_ids = np.concatenate([ids[k] for k in matches], 0) if matches else np.zeros((0, 2), dtype=np.int32)
+    return (torch.from_numpy(np.concatenate(xy, 0)), torch.from_numpy(np.concatenate(sc, 0)), torch.tensor(off, dtype=torch.int32),
+            torch.from_numpy(all_ids))
+
+
+def _post_worker(rank, world, port, q):
+    import itertools
+    import numpy as np
+    os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world),
+                       "LOCAL_RANK": str(rank)})
+    from detectorfreesfm_b200 import dist as D
+    from detectorfreesfm_b200.postprocess_dist import merge_keypoints_sharded
+    from oracle import postprocess_oracle as po
+    r, w, _ = D.init_from_env(backend="gloo")
+    pairs = [p for p in itertools.combinations(range(6), 2) if 5 not in p]       # image 5 never matched
+    matches, names = po.synth_matches(6, pairs, [0, 30, 120], seed=3, dup=0.4)
+    keys = list(matches.keys())
+    mine = D.shard(len(keys), r, w)                                               # strided, as the HP-1 bench shards pairs
+    local = {keys[i]: matches[keys[i]] for i in mine}
+    fk, fs, upd = merge_keypoints_sharded(local, mine, names, " ", local_merge=_oracle_flat_merge)
+    ref = po.merge_keypoints(matches, names, " ")
+    ok = all(np.array_equal(fk[n], ref[0][n]) and fk[n].shape == ref[0][n].shape and np.array_equal(fs[n], ref[1][n]) for n in names)
+    ok = ok and all(np.array_equal(upd[k], ref[2][k]) and upd[k].dtype == ref[2][k].dtype for k in local)
+    q.put((r, ok, len(local)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_postprocess_exchange_gloo_world2():
+    """Pairs strided over two ranks, images owned in blocks: all-to-all of the (pair, side) halves, merge per owner, ids back.
+    Bit-identical to the single-process oracle on every rank (scores summed in global pair order)."""
+    port = 31500 + os.getpid() % 2000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_post_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert [r[1] for r in res] == [True, True] and sum(r[2] for r in res) == 10
+
+
+def test_sharded_postprocess_single_process_path():
+    """Without torch.distributed the sharded entry point degenerates to the plain merge (same halves / sink-image plumbing)."""
+    import itertools
+    import numpy as np
+    from detectorfreesfm_b200.postprocess_dist import image_owner, merge_keypoints_sharded
+    from oracle import postprocess_oracle as po
+    matches, names = po.synth_matches(4, list(itertools.combinations(range(4), 2)), 60, seed=9)
+    fk, fs, upd = merge_keypoints_sharded(matches, list(range(len(matches))), names, " ", local_merge=_oracle_flat_merge)
+    ref = po.merge_keypoints(matches, names, " ")
+    assert all(np.array_equal(fk[n], ref[0][n]) and np.array_equal(fs[n], ref[1][n]) for n in names)
+    assert all(np.array_equal(upd[k], ref[2][k]) for k in matches)
+    assert image_owner(10, 4).tolist() == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3] and image_owner(3, 8).tolist() == [0, 1, 2]
