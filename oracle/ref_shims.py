@@ -225,6 +225,30 @@ def multiview_config(window=15, left_window=7):
     }
 
 
+class _Remote:
+    """stand-in for ray.remote: ``@ray.remote`` and ``@ray.remote(...)`` both leave the function as it is"""
+    def __call__(self, *a, **k):
+        if len(a) == 1 and callable(a[0]) and not k:
+            return a[0]
+        return lambda f: f
+
+
+def _stub_ray():
+    """ray is not installed in this image: an inert module with ``remote`` and ``actor.ActorHandle`` (decorators / annotations only)"""
+    m = sys.modules.get("ray")
+    if m is not None and getattr(m, "__file__", None):
+        return                                   # a real ray
+    try:
+        if m is None:
+            import ray  # noqa: F401
+            return
+    except Exception:
+        pass
+    ray_mod = _mod("ray", remote=_Remote())
+    ray_mod.__path__ = []
+    ray_mod.actor = _mod("ray.actor", ActorHandle=object)
+
+
 def import_postprocess():
     """-> (Match2Kpts, keypoint_worker, update_matches, transform_keypoints) from src/coarse_match.
 
@@ -244,15 +268,7 @@ def import_postprocess():
     ds.__path__ = []
     _mod("src.dataset.coarse_matching_dataset", CoarseMatchingDataset=object)
 
-    class _Remote:
-        def __call__(self, *a, **k):
-            if len(a) == 1 and callable(a[0]) and not k:
-                return a[0]
-            return lambda f: f
-    try:
-        import ray  # noqa: F401
-    except Exception:
-        _mod("ray", remote=_Remote())
+    _stub_ray()
     try:
         import pytorch_lightning  # noqa: F401
     except Exception:
@@ -283,3 +299,38 @@ def import_image_utils():
         except Exception:
             _mod(name)
     return importlib.import_module("src.dataset.utils")
+
+
+def import_refine_worker(dataset_cls=None):
+    """-> the reference's src/post_optimization/matcher_model/multiview_match_worker.py module (matchWorker, extract_results,
+    UpdatedQueryPts) for CPU comparisons of the host loop.
+
+    ``MatchingMultiviewData`` is replaced by ``dataset_cls`` (the chunk construction is row b2 / 8(f)-2, not under test here),
+    ``dict_to_cuda`` by the identity (no GPU in the build container); ray / pytorch_lightning / omegaconf are inert stubs."""
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    utils = _mod("src.utils")
+    utils.__path__ = []
+    _mod("src.utils.data_io", dict_to_cuda=lambda d: d)
+    mm = _mod("src.MultiviewMatcher")
+    mm.__path__ = []
+    _mod("src.MultiviewMatcher.MultiviewMatcher", MultiviewMatcher=object)
+    po_ = _mod("src.post_optimization")
+    po_.__path__ = [os.path.join(REF, "src", "post_optimization")]
+    _mod("src.post_optimization.data_construct", MatchingMultiviewData=dataset_cls if dataset_cls is not None else object)
+    mmod = _mod("src.post_optimization.matcher_model")
+    mmod.__path__ = [os.path.join(REF, "src", "post_optimization", "matcher_model")]
+
+    _stub_ray()
+    try:
+        import pytorch_lightning  # noqa: F401
+    except Exception:
+        _mod("pytorch_lightning", seed_everything=lambda s: None)
+    try:
+        import omegaconf  # noqa: F401
+    except Exception:
+        _mod("omegaconf", OmegaConf=object)
+    return importlib.import_module("src.post_optimization.matcher_model.multiview_match_worker")

@@ -6,6 +6,7 @@ Fixtures (small, fp32, torch.save):
   loftr_small.pt       LoFTR coarse_only on a 64x80 pair: conf-matrix digest, match ids, mkpts, mconf, feature digests
   multiview_small.pt   MultiviewMatcher on a 24-track chunk: refined points + std
   postprocess_small.pt Match2Kpts + keypoint_worker + update_matches + transform_keypoints on synthetic matches of 5 images
+  refine_worker_small.pt  matchWorker (the reference's refinement host loop) on three small chunks with a stand-in matcher
   image_small.pt       read_grayscale (cv2 decode of a PNG written here, PIL-LANCZOS resize, /255) on three synthetic images
 """
 import os
@@ -78,7 +79,28 @@ def main():
     # ---- match -> keypoint -> index post-processing (coarse_match.py:203-237), reference functions themselves
     torch.save(postprocess_golden(), os.path.join(HERE, "postprocess_small.pt"))
     torch.save(image_golden(), os.path.join(HERE, "image_small.pt"))
+    torch.save({"results": reference_refine_worker()}, os.path.join(HERE, "refine_worker_small.pt"))
     print("golden fixtures written to", HERE)
+
+
+def reference_refine_worker():
+    """the reference's matchWorker itself (multiview_match_worker.py:111-150): chunk dataset replaced by a list, dict_to_cuda by
+    the identity, the matcher by tests.util.StandInRefiner -> list of [K,4] arrays"""
+    class ListDataset(torch.utils.data.Dataset):
+        colmap_images = {i: None for i in range(4)}
+
+        def __init__(self, colmap_dataset, cfgs, worker_split_idxs=None):
+            self.chunks = util.worker_chunks()
+
+        def __len__(self):
+            return len(self.chunks)
+
+        def __getitem__(self, i):
+            return self.chunks[i]
+
+    mod = ref_shims.import_refine_worker(ListDataset)
+    mod.DataLoader = lambda ds, num_workers=0, pin_memory=False: torch.utils.data.DataLoader(ds, num_workers=0)
+    return mod.matchWorker(None, util.StandInRefiner(), verbose=False)
 
 
 def reference_read_grayscale(image_u8, resize, df, tmpdir):

@@ -132,3 +132,18 @@ def test_host_lanczos_tables_equal_oracle_tables():
     for args in [(800, 600, (512,), 8, False), (600, 800, (1200,), 8, False), (640, 480, (-1,), 8, False), (640, 480, (320, 200), None, False),
                  (300, 200, (1200,), 8, True)]:
         assert ip.process_resize(*args) == io.process_resize(*args)
+
+
+def test_refine_worker_loop_vs_golden():
+    """Row b1 host loop (refine_stage.match_worker) vs the [K,4] arrays the reference's matchWorker produced for the same chunks
+    and stand-in matcher; with freeze=True (the evident intent of UpdatedQueryPts) later chunks hold frozen nodes."""
+    import numpy as np
+    from detectorfreesfm_b200 import refine_stage as rs
+    from tests import util
+    ref = torch.load(os.path.join(GOLD, "refine_worker_small.pt"), weights_only=False)["results"]
+    loader = torch.utils.data.DataLoader(util.worker_chunks(), num_workers=0)
+    got = rs.match_worker(loader, util.StandInRefiner(), range(4), device=torch.device("cpu"))
+    assert len(got) == len(ref) == 3 and all(np.array_equal(a, b) for a, b in zip(ref, got))
+    frozen = rs.match_worker(torch.utils.data.DataLoader(util.worker_chunks(), num_workers=0), util.StandInRefiner(), range(4),
+                             device=torch.device("cpu"), freeze=True)
+    assert frozen[0].shape == got[0].shape and frozen[1].shape[0] < got[1].shape[0]

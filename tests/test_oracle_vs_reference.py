@@ -92,3 +92,19 @@ def test_image_oracle_matches_reference_read_grayscale(tmp_path):
         t, scales, hw = reference_read_grayscale(img, resize, df, str(tmp_path))
         to, so, ho = io.read_grayscale_from_array(img, resize, df=df)
         assert t.dtype == to.dtype and torch.equal(t, to) and torch.equal(scales, so) and torch.equal(hw, ho)
+
+
+def test_refine_worker_loop_matches_reference_match_worker():
+    """Row b1: the reference's matchWorker (its real code, with the chunk dataset replaced by a list and dict_to_cuda by the
+    identity) and detectorfreesfm_b200.refine_stage.match_worker give identical [K,4] arrays for the same chunks and the same
+    (deterministic stand-in) matcher -- including the fact that UpdatedQueryPts never freezes anything in the reference."""
+    import numpy as np
+    from detectorfreesfm_b200 import refine_stage as rs
+    from tests import util
+    from tests.golden.make_golden import reference_refine_worker
+    ref = reference_refine_worker()
+    got = rs.match_worker(torch.utils.data.DataLoader(util.worker_chunks(), num_workers=0), util.StandInRefiner(), range(4),
+                          device=torch.device("cpu"))
+    assert len(ref) == len(got) == 3
+    for a, b in zip(ref, got):
+        assert a.shape == b.shape and a.shape[1] == 4 and np.array_equal(a, b)

@@ -87,3 +87,30 @@ def synth_chunk(M=64, n_img=6, max_views=5, hw=(120, 160), seed=0, scales=None, 
         "query_movable_mask": movable[None],
         "scales_relative": torch.ones(1, Nq + 1, M), "view_point_vector": torch.zeros(1, Nq + 1, M, 3),
     }
+
+
+def worker_chunks(seeds=(4, 5, 6)):
+    """Chunk items as MatchingMultiviewData.__getitem__ yields them (no batch dimension; the DataLoader adds it) for the
+    refinement-worker loop tests: colmap ids included, the same reference nodes recur in every chunk."""
+    out = []
+    for seed in seeds:
+        c = synth_chunk(M=12, n_img=4, max_views=3, seed=seed)
+        item = {k: (v[0] if torch.is_tensor(v) else v) for k, v in c.items() if k != "images"}
+        item["images"] = [im[0] for im in c["images"]]
+        item["query_img_ids"] = item["query_img_idxs"].clone() % 2
+        item["query_pt2d_idxs"] = torch.arange(12) % 5
+        item["reference_img_ids"] = item["reference_img_idxs"].clamp(min=0)
+        item["reference_pt2d_idxs"] = (torch.arange(item["reference_img_idxs"].numel()).view_as(item["reference_img_idxs"]) * 7 + seed) % 101
+        out.append(item)
+    return out
+
+
+class StandInRefiner:
+    """Deterministic stand-in honouring the HP-2 contract (host-loop tests only; no kernels involved)."""
+
+    def cuda(self):
+        return self
+
+    def __call__(self, data):
+        data["query_points_refined"] = data["query_points"] + 0.25
+        data["reference_points_refined"] = [data["reference_points_coarse"] * 0 + 1.0, data["reference_points_coarse"] - 0.5]
