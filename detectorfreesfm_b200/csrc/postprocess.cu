@@ -12,6 +12,9 @@
 //   sort #2 over uniques (stable): by ~bits(sum) (descending score), then by image -> rank r = global keypoint index
 //   id(u) = r - first rank of u's image; match_ids[t][side] = id(u(o))
 //
+// Not reproduced: a pair of an image with itself (never produced by the pair generators) would accumulate its two sides
+// row-interleaved here and side after side in the reference -- the same float64 sum unless it is inexact.
+//
 // HBM-bound integer work: every pass streams 12-byte (key, value) records; no tensor cores involved.
 #include <algorithm>
 #include <memory>
