@@ -32,7 +32,10 @@ from tests import util  # noqa: E402  (seeded synthetic inputs shared with the t
 HW = 832
 N_IMAGES = 8
 METRIC = "image-pairs/s coarse-match (hp2: tracks/s refinement)"
-WORKLOAD = f"C2 demo scene: {N_IMAGES} synthetic {HW}x{HW} images, exhaustive 28 pairs per rank, LoFTR coarse_only, thr 0.2"
+NOISE = 0.025
+WORKLOAD = (f"C2 demo scene: {N_IMAGES} overlapping synthetic views {HW}x{HW} (crops of one low-pass noise image at 8-px-aligned offsets + "
+            f"N(0,{NOISE}) per view), exhaustive 28 pairs per rank, LoFTR coarse_only, shipped thr 0.2 / temperature 0.1, BN-calibrated "
+            "seeded weights (tests/weights.py) -> O(10^3) matches per pair; the step ends with the match->keypoint merge of its own matches")
 
 
 def conv_gemm_flops(H, W):
@@ -117,28 +120,79 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import loftr_oracle as lo
-    from oracle import weights
+    from oracle import postprocess_oracle as po
+    from tests import weights
     torch.set_num_threads(cpu_threads())
-    sd = weights.loftr_state_dict(0)
-    im0, im1 = util.synth_image(HW, HW, 1000), util.synth_image(HW, HW, 1001)
-    data = {"image0": im0, "image1": im1, "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
+    sd = weights.loftr_state_dict(0, calibrated=True)
+    images, _ = util.synth_scene(N_IMAGES, HW, HW, 1000, noise=NOISE)
+    data = {"image0": images[0], "image1": images[1], "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
     ref_cfg = {"compute_unused_fine_branch": True}  # the reference evaluates the unused 1/2-res FPN branch too
+
+    def ref_step():
+        out = lo.loftr_forward(data, sd, ref_cfg)
+        m = np.concatenate([out["mkpts0_f"].numpy(), out["mkpts1_f"].numpy(), out["mconf"].numpy()[:, None]], -1).astype(np.float32)
+        po.merge_keypoints({"im0 im1": m}, ["im0", "im1"], " ")
+        return m.shape[0]
+
     for _ in range(min(args.warmup, 1)):
-        lo.loftr_forward(data, sd, ref_cfg)
+        ref_step()
     steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(steps):
-        lo.loftr_forward(data, sd, ref_cfg)
+        n_matches = ref_step()
     dt = time.perf_counter() - t0
     v = steps / dt
+    hp2 = None if args.skip_hp2 else hp2_cpu_baseline(256)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "bounded: 1 pair of the workload per step, PyTorch CPU fp32"},
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "bounded: 1 pair of the workload per step (+ the merge of its matches), PyTorch CPU fp32"},
         "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{steps} x one {HW}x{HW} pair, oracle/loftr_oracle.py (PyTorch CPU fp32)"},
+                         "sample": f"{steps} x one {HW}x{HW} pair ({n_matches} matches), oracle/loftr_oracle.py + postprocess_oracle.py (PyTorch CPU fp32 / numpy)"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        "matches_per_pair": n_matches, "hp2": hp2,
     }))
+
+
+def hp2_chunk(tracks, seed):
+    return util.synth_chunk(M=tracks, n_img=10, max_views=9, hw=(600, 800), seed=seed, scales=torch.ones(1, 10, 2))
+
+
+def chunk_slice(chunk, sl):
+    """a contiguous slice of tracks of a chunk dict (tracks stay sorted by valid-view count)"""
+    sub = dict(chunk)
+    for k in ("query_points", "query_img_idxs", "query_movable_mask"):
+        sub[k] = chunk[k][:, sl].contiguous()
+    for k in ("reference_points_coarse", "track_valid_mask", "reference_img_idxs", "scales_relative", "view_point_vector"):
+        sub[k] = chunk[k][:, :, sl].contiguous()
+    return sub
+
+
+def hp2_cpu_baseline(n_sub):
+    """HP-2 reference CPU path: the oracle port (validated against the reference MultiviewMatcher) + the reference's own
+    RoIAlign C++ when oracle/_ref holds it, on an n_sub-track slice taken from the middle of the C3 chunk (tracks are sorted by
+    view count, so the middle slice has the chunk's mean patches per track to within a few %)."""
+    from oracle import multiview_oracle as mo
+    from tests import weights
+    torch.set_num_threads(cpu_threads())
+    sd = weights.multiview_state_dict(0)
+    chunk = hp2_chunk(2000, 11)
+    lo_ = (2000 - n_sub) // 2
+    sub = chunk_slice(chunk, slice(lo_, lo_ + n_sub))
+    patches_sub = int(sub["track_valid_mask"].sum()) + n_sub
+    patches_full = int(chunk["track_valid_mask"].sum()) + 2000
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 2 and (reps == 0 or time.perf_counter() - t0 < 20):
+        mo.multiview_forward(sub, sd, 15, 7)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    kind = "C restatement of the reference RoIAlign, pinned bit-exact to oracle/_ref"
+    return {"value": n_sub / dt, "unit": "tracks/s", "cores": torch.get_num_threads(), "kind": "port",
+            "value_patch_scaled": (patches_sub / dt) * (2000.0 / patches_full),
+            "sample": f"{reps} x a {n_sub}-track slice ({patches_sub} patches; full chunk {patches_full}) of the C3 chunk, oracle/multiview_oracle.py "
+                      f"(PyTorch CPU fp32; {kind}); value_patch_scaled = tracks/s of the full chunk at the same patches/s"}
+
 
 
 # ----------------------------------------------------------------------------------------------------- our arm
@@ -157,9 +211,9 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher, _lib
+    from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher, KeypointMerger, _lib
     from detectorfreesfm_b200 import dist as D
-    from oracle import weights
+    from tests import weights
     rank, world, local = D.init_from_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -169,11 +223,20 @@ def main():
 
     # ------------------------------------------------------------------ HP-1 workload: one scene per rank
     matcher = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=2 * N_IMAGES).cuda(local).eval()
-    matcher.load_state_dict(weights.loftr_state_dict(0))
-    host_images = [util.synth_image(HW, HW, 1000 * (rank + 1) + i).pin_memory() for i in range(N_IMAGES)]
+    matcher.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
+    host_images = [im.pin_memory() for im in util.synth_scene(N_IMAGES, HW, HW, 1000 * (rank + 1), noise=NOISE)[0]]
     dev_images = [im.to(dev) for im in host_images]
     pairs = [(i, j) for i in range(N_IMAGES) for j in range(i + 1, N_IMAGES)]
     ones = torch.ones(1, 2, device=dev)
+    merger = KeypointMerger(dev)
+    pair_img = torch.tensor(pairs, dtype=torch.int32, device=dev)
+    m_stats = {}
+
+    def merge_step(out):
+        """the match -> keypoint -> index merge (coarse_match.py:203-237) of THIS step's matches, still on the device"""
+        counts = torch.tensor([0] + [int(o.shape[0]) for o in out], dtype=torch.int64)
+        m_stats["counts"] = counts[1:].tolist()
+        return merger.merge(torch.cat(out, 0), torch.cumsum(counts, 0), pair_img, N_IMAGES)
 
     def step_resident(cached):
         """inputs resident in HBM; returns the per-pair (M,5) device arrays"""
@@ -185,6 +248,7 @@ def main():
                 data["pair_key"] = ((f"im{i}",), (f"im{j}",))
             matcher(data)
             out.append(torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1))
+        m_stats["merged"] = merge_step(out)
         return out
 
     h2d = d2h = 0
@@ -194,7 +258,7 @@ def main():
         nonlocal h2d, d2h
         matcher._cache.clear()
         h2d = d2h = 0
-        res = []
+        res, dev_out = [], []
         for (i, j) in pairs:
             a, b = host_images[i].to(dev, non_blocking=True), host_images[j].to(dev, non_blocking=True)
             h2d += a.numel() * 4 + b.numel() * 4
@@ -202,9 +266,13 @@ def main():
             if cached:
                 data["pair_key"] = ((f"im{i}",), (f"im{j}",))
             matcher(data)
-            m = np.concatenate([data["mkpts0_f"].cpu().numpy(), data["mkpts1_f"].cpu().numpy(), data["mconf"].cpu().numpy()[:, None]], -1)
+            md = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
+            dev_out.append(md)
+            m = md.cpu().numpy()
             d2h += m.nbytes + 4  # + the match-count readback that sizes the arrays
             res.append(m)
+        kp = [t.cpu() for t in merge_step(dev_out)]   # keypoints, scores, per-image offsets, per-match keypoint ids -> host
+        d2h += sum(t.numel() * t.element_size() for t in kp)
         return res
 
     def timed(fn, steps, gather):
@@ -262,24 +330,33 @@ def main():
     # ------------------------------------------------------------------ HP-2: one refinement chunk (C3)
     hp2 = None
     if not args.skip_hp2:
-        from tests.test_refine_gpu import multiview_config, to_cuda
+        multiview_config, to_cuda = util.multiview_config, util.to_cuda
         rm = B200MultiviewMatcher(multiview_config(15, 7), test=True).cuda(local).eval()
         rm.load_state_dict(weights.multiview_state_dict(0))
-        chunk = util.synth_chunk(M=args.hp2_tracks, n_img=10, max_views=9, hw=(600, 800), seed=11 + rank, scales=torch.ones(1, 10, 2))
-        host_imgs = [im.pin_memory() for im in chunk["images"]]
+        chunk = hp2_chunk(args.hp2_tracks, 11 + rank)
         n_patches = int(chunk["track_valid_mask"].sum()) + args.hp2_tracks
         cd = to_cuda(chunk)
+        # the chunk as MatchingMultiviewData + DataLoader hand it over: every tensor on the HOST (pinned)
+        host_chunk = {k: ([im.pin_memory() for im in v] if isinstance(v, list) else (v.pin_memory() if torch.is_tensor(v) else v))
+                      for k, v in chunk.items()}
+        h2d_2 = sum(t.numel() * t.element_size() for v in host_chunk.values() for t in (v if isinstance(v, list) else [v]) if torch.is_tensor(t))
 
         def chunk_resident():
             d = dict(cd)
             rm(d)
             return d
 
+        d2h_2 = 0
+
         def chunk_e2e():
-            d = dict(cd)
-            d["images"] = [im.to(dev, non_blocking=True) for im in host_imgs]
+            """what matchWorker does per chunk (multiview_match_worker.py:111-150): the whole host dict -> device, matcher, results -> host"""
+            nonlocal d2h_2
+            d = {k: ([im.to(dev, non_blocking=True) for im in v] if isinstance(v, list) else (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v))
+                 for k, v in host_chunk.items()}
             rm(d)
-            return d["query_points_refined"].cpu(), d["reference_points_refined"][-1].cpu()
+            outs = (d["query_points_refined"].cpu(), d["reference_points_refined"][-1].cpu(), d["std"][-1].cpu())
+            d2h_2 = sum(t.numel() * t.element_size() for t in outs)
+            return outs
 
         for _ in range(2):
             chunk_resident()
@@ -297,24 +374,25 @@ def main():
         hp2 = {"metric": "tracks/s refinement", "value": args.hp2_tracks * k2 * world / (ms2 * 1e-3), "unit": "tracks/s",
                "ms_per_chunk": ms2 / k2, "tracks_per_chunk": args.hp2_tracks, "patches_per_chunk": n_patches,
                "e2e": {"value": args.hp2_tracks * k2 * world / (ms2_e2e * 1e-3), "unit": "tracks/s",
-                       "h2d_bytes_per_step": sum(im.numel() * 4 for im in host_imgs), "d2h_bytes_per_step": args.hp2_tracks * 2 * 4 * 10},
+                       "h2d_bytes_per_step": h2d_2, "d2h_bytes_per_step": d2h_2,
+                       "note": "host chunk dict (pinned) -> device, matcher call, refined points + std -> host; copies the host shim makes "
+                               "internally (index arrays staged for the C ABI) are inside the timed region but not in these byte counts"},
                "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,split,ConvEpi> (S2DNet patch convolutions, persistent CTA pairs)",
                             "achieved": pconv_alg / (pc_ms * 1e-3) / 1e12 if pc_ms else None, "peak": peaks["tflops"], "unit": "TFLOP/s",
                             "frac": pconv_alg / (pc_ms * 1e-3) / 1e12 / peaks["tflops"] if pc_ms else None,
                             "note": "algorithmic = FLOPs the reference executes (1.02 GFLOP/patch); the engine skips the part of the 5x5 "
                                     "adapter outside the centre window and runs 3 fp16 passes",
                             "kernel_ms_per_chunk": {k: round(v[1], 3) for k, v in sorted(prof2.items())}}}
+        if rank == 0 and world == 1 and not args.skip_cpu:
+            hp2["cpu_baseline"] = hp2_cpu_baseline(256)
 
     # ------------------------------------------------------------------ match -> keypoint -> index post-processing
     post = None
     if not args.skip_post:
         try:
-            from detectorfreesfm_b200 import KeypointMerger
-            from oracle import postprocess_oracle as po
             n_img, m_pair = 64, 2000
             pairs = list(itertools.combinations(range(n_img), 2))
-            pm, names = po.synth_matches(n_img, pairs, m_pair, seed=5 + rank, dup=0.25)
-            merger = KeypointMerger(dev)
+            pm, names = util.synth_matches(n_img, pairs, m_pair, seed=5 + rank, dup=0.25)
             rows_host = torch.from_numpy(np.concatenate(list(pm.values()), 0)).pin_memory()
             rows_dev = rows_host.to(dev)
             counts = np.array([v.shape[0] for v in pm.values()], dtype=np.int64)
@@ -351,8 +429,9 @@ def main():
                                  "traffic": None, "launches": sc_cnt,
                                  "kernel_ms_per_call": {k: round(v[1], 3) for k, v in sorted(prof3.items())}}}
             if rank == 0 and world == 1 and not args.skip_cpu:
+                from oracle import postprocess_oracle as po
                 sub_pairs = list(itertools.combinations(range(12), 2))
-                sub, sub_names = po.synth_matches(12, sub_pairs, m_pair, seed=5, dup=0.25)
+                sub, sub_names = util.synth_matches(12, sub_pairs, m_pair, seed=5, dup=0.25)
                 t0 = time.perf_counter()
                 reps = 0
                 while reps < 3 and time.perf_counter() - t0 < 15:
@@ -371,10 +450,9 @@ def main():
     if not args.skip_img:
         try:
             from detectorfreesfm_b200.image_pipeline import GpuImageReader, process_resize
-            from oracle import image_oracle as imo
             rd = GpuImageReader(dev)
             src_hw = (3000, 4000)                       # a 12 MP photo, demo config: longest side -> 1200, df = 8
-            photo = imo.synth_photo(src_hw[0], src_hw[1], seed=3 + rank)
+            photo = util.synth_photo(src_hw[0], src_hw[1], seed=3 + rank)
             size = process_resize(src_hw[1], src_hw[0], (1200,), 8)
             photo_dev = torch.from_numpy(photo).to(dev)
             n_img = 8
@@ -421,7 +499,7 @@ def main():
     if rank == 0 and world == 1 and not args.skip_cpu:
         from oracle import loftr_oracle as lo
         torch.set_num_threads(cpu_threads())
-        sd = weights.loftr_state_dict(0)
+        sd = weights.loftr_state_dict(0, calibrated=True)
         data = {"image0": host_images[0], "image1": host_images[1], "scale0": torch.ones(1, 2), "scale1": torch.ones(1, 2)}
         t0 = time.perf_counter()
         n_cpu = 0
@@ -446,6 +524,8 @@ def main():
             "value_cached": n_pairs * K / (ms_cached * 1e-3),
             "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "value_cached": n_pairs * K / (ms_e2e_cached * 1e-3)},
+            "matches_per_pair": {"mean": float(np.mean(m_stats["counts"])), "min": int(min(m_stats["counts"])), "max": int(max(m_stats["counts"])),
+                                 "keypoints_merged": int(m_stats["merged"][0].shape[0])},
             "gpu_launches": total_launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "algorithmic_gflop_per_pair": pair_flops(HW, HW) / 1e9, "hp2": hp2, "post": post, "image_pipeline": img_leg,
         }

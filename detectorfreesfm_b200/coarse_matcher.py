@@ -110,11 +110,11 @@ class B200LoFTR(torch.nn.Module):
         if self.fine:
             feat_f = torch.empty((H // 2) * (W // 2), 128, device=self._device, dtype=torch.float32)
             _lib.check(self._lib.dfsfm_coarse_features_fine(self._h, _lib.ptr(image), H, W, _lib.ptr(self._pe_tokens(h, w)), _lib.ptr(tokens),
-                                                            _lib.ptr(feat_f), _lib.stream_ptr()))
+                                                            _lib.ptr(feat_f), _lib.stream_ptr(self._device)))
             out = (tokens, feat_f)
         else:
             _lib.check(self._lib.dfsfm_coarse_features(self._h, _lib.ptr(image), H, W, _lib.ptr(self._pe_tokens(h, w)), _lib.ptr(tokens),
-                                                       _lib.stream_ptr()))
+                                                       _lib.stream_ptr(self._device)))
             out = tokens
         if key is not None:
             self._cache[key] = out
@@ -131,13 +131,13 @@ class B200LoFTR(torch.nn.Module):
             i32, j32 = i_ids.to(torch.int32).contiguous(), j_ids.to(torch.int32).contiguous()
             _lib.check(self._lib.dfsfm_coarse_fine_match(self._h, _lib.ptr(feat_f0), hw0_f[0], hw0_f[1], _lib.ptr(feat_f1), hw1_f[0], hw1_f[1],
                                                          _lib.ptr(feat_c0), hw0_c[1], _lib.ptr(feat_c1), hw1_c[1], _lib.ptr(i32), _lib.ptr(j32), M,
-                                                         _lib.ptr(coords), _lib.ptr(std), _lib.stream_ptr()))
+                                                         _lib.ptr(coords), _lib.ptr(std), _lib.stream_ptr(self._device)))
         return coords, std
 
     def transform(self, feat0, feat1):
         """LocalFeatureTransformer (8 layers) in place on [L,256], [S,256] fp32 tokens."""
         _lib.check(self._lib.dfsfm_coarse_transformer(self._h, _lib.ptr(feat0), feat0.shape[0], _lib.ptr(feat1), feat1.shape[0],
-                                                      _lib.stream_ptr()))
+                                                      _lib.stream_ptr(self._device)))
         return feat0, feat1
 
     def coarse_match(self, feat0, hw0_c, feat1, hw1_c, return_conf=False):
@@ -150,7 +150,7 @@ class B200LoFTR(torch.nn.Module):
         conf = torch.empty(L, S, device=self._device, dtype=torch.float32) if return_conf else None
         _lib.check(self._lib.dfsfm_coarse_match(self._h, _lib.ptr(feat0), hw0_c[0], hw0_c[1], _lib.ptr(feat1), hw1_c[0], hw1_c[1],
                                                 self.thr, self.border_rm, self.temperature, _lib.ptr(i_ids), _lib.ptr(j_ids),
-                                                _lib.ptr(mconf), _lib.ptr(count), cap, _lib.ptr(conf), _lib.stream_ptr()))
+                                                _lib.ptr(mconf), _lib.ptr(count), cap, _lib.ptr(conf), _lib.stream_ptr(self._device)))
         n = int(count.item())  # the one device sync per pair (the reference's torch.where does the same)
         return i_ids[:n].long(), j_ids[:n].long(), mconf[:n], conf
 
@@ -158,6 +158,17 @@ class B200LoFTR(torch.nn.Module):
     @torch.no_grad()
     def forward(self, data):
         """Same contract as LoFTR.forward (loftr.py:29-81): updates ``data`` in place."""
+        if not self._h:
+            raise _lib.DfsfmError("B200LoFTR: call .cuda() before forward (there is no CPU path)")
+        with torch.cuda.device(self._device):   # the engine's kernels, workspaces and stream all belong to its own device
+            return self._forward(data)
+
+    def clear_cache(self):
+        """Drop the per-image feature cache.  Entries are keyed by (pair_key name, H, W): a caller that re-uses a name for
+        different pixels (another dataset root with the same relative paths) must clear it between scenes."""
+        self._cache.clear()
+
+    def _forward(self, data):
         if not self._h:
             raise _lib.DfsfmError("B200LoFTR: call .cuda() before forward (there is no CPU path)")
         if self._packed is None:

@@ -27,7 +27,10 @@ def match_worker(subset_ids, image_lists, covis_pairs_out, cfgs, matcher, detect
     if dataset is None:
         dataset = B200CoarseMatchingDataset(cfgs["data"], image_lists, covis_pairs_out, subset_ids)
     loader = torch.utils.data.DataLoader(dataset, num_workers=0)      # items are CUDA tensors (no worker processes)
-    rounding = args["model"]["type"] != "coarse_only" and args.get("round_matches_ratio") is not None   # :134
+    # :134 tests ``args['model']['type'] is not 'coarse_only'`` -- an IDENTITY test against a literal, true for every run-time
+    # string (hydra hands over a fresh str object), so the reference rounds whenever a ratio is configured, whatever the match
+    # type.  The shipped coarse_only configs set the ratio to null; coarse points are multiples of 8 px anyway.
+    rounding = args.get("round_matches_ratio") is not None
     matches = {}
     for data in loader:
         f_name0, f_name1 = data["pair_key"][0][0], data["pair_key"][1][0]

@@ -107,9 +107,7 @@ class CoarseEngine {
 
     template <int BN>
     void conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st);
-    // q_mode (cross layers, DFSFM_XQ=1): 1 = also project q for the source rows (they are the next call's x), 2 = q of x is already there
-    void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st,
-                    int q_mode = 0);
+    void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st);
 };
 
 static int kv_tok() {  // tokens per KV-partial CTA (A/B: DFSFM_KV_TOK)
@@ -120,16 +118,6 @@ static int kv_tok() {  // tokens per KV-partial CTA (A/B: DFSFM_KV_TOK)
         if (v < 16) v = 16;
     }
     return v;
-}
-// DFSFM_XQ=1 (off by default: not yet measured on hardware): a cross layer projects q of image 1 together with its k, v in the
-// first call -- image 1 is only modified by the second call -- which saves one GEMM launch per cross layer.
-static bool cross_q_merge() {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("DFSFM_XQ");
-        v = (e && e[0] == '1') ? 1 : 0;
-    }
-    return v == 1;
 }
 static bool lin_bn128() {  // A/B switch: 128-wide N tiles for the wide linears (QKV, KV, mlp.0): twice the tiles, better last-round fill
     static int v = -1;
@@ -411,7 +399,7 @@ static bool res_hl() {
 }
 
 void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count,
-                              cudaStream_t st, int q_mode) {
+                              cudaStream_t st) {
     const std::string p = "tr." + std::to_string(li);
     GemmCore c;
     memset(&c, 0, sizeof(c));
@@ -435,7 +423,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c, e, 768, st, "lin"); }
             else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
         } else {
-            if (q_mode != 2) {  // q of the attending tokens (mode 2: projected by the previous call together with its k, v)
+            {   // q of the attending tokens
                 for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
                 c.M = xn; c.b_row0 = 0;
                 e.M = xn; e.N = 256; e.elu_cols = 256; e.out_f32 = qkv + static_cast<long long>(x0) * 768; e.out_col0 = 0;
@@ -444,14 +432,9 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], s0, sn);
             c.M = sn;
             e.M = sn; e.out_f32 = qkv + static_cast<long long>(s0) * 768;
-            if (q_mode == 1) {  // q, k, v of the source rows in one launch: the source is the next call's x and is not modified before
-                c.b_row0 = 0; e.N = 768; e.elu_cols = 512; e.out_col0 = 0;
-                launch_gemm_counted<256, true, LinEpi>(maps, c, e, 768, st, "lin");
-            } else {
-                c.b_row0 = 256; e.N = 512; e.elu_cols = 256; e.out_col0 = 256;
-                if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c, e, 512, st, "lin"); }
-                else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
-            }
+            c.b_row0 = 256; e.N = 512; e.elu_cols = 256; e.out_col0 = 256;
+            if (lin_bn128()) { maps.b = make_tmap(params.mat(p + ".qkv"), bbox(128)); launch_gemm_counted<128, true, LinEpi>(maps, c, e, 512, st, "lin"); }
+            else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
         }
     }
     {   // KV state(s): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
@@ -537,9 +520,8 @@ void CoarseEngine::transformer(float* f0, int L, float* f1, int S, cudaStream_t 
         if ((li % 2) == 0) {  // layer_names = ['self','cross'] * 4 (default.py:22): both images in one pass
             layer_call(li, true, 0, L + S, 0, L + S, 0, 2, 0, mx, st);
         } else {
-            const bool xq = cross_q_merge();
-            layer_call(li, false, 0, L, L, S, 1, 1, 2, mx, st, xq ? 1 : 0);  // feat0 attends feat1
-            layer_call(li, false, L, S, 0, L, 0, 1, 3, mx, st, xq ? 2 : 0);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
+            layer_call(li, false, 0, L, L, S, 1, 1, 2, mx, st);  // feat0 attends feat1
+            layer_call(li, false, L, S, 0, L, 0, 1, 3, mx, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
         }
     }
     DFSFM_CUDA(cudaMemcpyAsync(f0, tok_.xf, static_cast<size_t>(L) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));

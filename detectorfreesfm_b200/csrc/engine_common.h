@@ -83,11 +83,8 @@ inline bool fused_mlp_enabled() {
 }
 inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long long T, const HL& w0, const HL& w2, const float* gamma,
                                 const float* beta, float* xf, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        DFSFM_CUDA(cudaFuncSetAttribute(mlp128_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemBytes));
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(mlp128_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemBytes));
     MlpMaps maps;
     maps.x = make_tmap(x.hi + row0 * 128, 128, T, x.plane_elems(), 128);
     maps.m1 = make_tmap(m1.hi + row0 * 128, 128, T, m1.plane_elems(), 128);

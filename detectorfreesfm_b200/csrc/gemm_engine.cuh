@@ -602,8 +602,15 @@ struct LinEpiParams {
     __half* out_hi;
     __half* out_lo;
     int out_ld;
-    int dbg;             // tuning aid (DFSFM_LIN_DBG): 1 no global stores, 2 no residual loads, 4 no LN statistics pass, 8 no column blocks
+#ifdef DFSFM_LIN_DEBUG
+    int dbg;             // tuning builds only (-DDFSFM_LIN_DEBUG, env DFSFM_LIN_DBG): 1 no global stores, 4 no LN statistics pass, 8 no column blocks
+#endif
 };
+#ifdef DFSFM_LIN_DEBUG
+#define DFSFM_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define DFSFM_DBG(p, bit) false
+#endif
 
 struct LinEpi {
     using Params = LinEpiParams;
@@ -613,7 +620,7 @@ struct LinEpi {
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx,
                                                const EpiCtx& ctx) {
         if constexpr (kCorr == 0) {  // engine 2 (engine 1 keeps a separate correction accumulator and has no staging buffers)
-            if (p.dbg & 8) return;
+            if (DFSFM_DBG(p, 8)) return;
             // generic fallback (the engines launch the LinEpiS specialisations instead, see launch_gemm_counted)
             if (p.mode == LIN_LN) {
                 if (p.resid != nullptr) run_ln_staged<BN, 1>(p, tmem_warp, row0, lane, n0, cb, ctx);
@@ -719,7 +726,7 @@ struct LinEpi {
         return *reinterpret_cast<const float4*>(stg + rl * 128 + ((ch ^ (rl & 7)) << 4));
     }
     static __device__ __forceinline__ void store_out(const Params& p, int r, int col, const float4& w) {
-        if (p.dbg & 1) return;
+        if (DFSFM_DBG(p, 1)) return;
         if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(r) * p.out_f32_ld + p.out_col0 + col) = w;
         if (p.out_hi) {
             uint2 uh, ul;
@@ -835,7 +842,7 @@ struct LinEpi {
         }
         tmem_ld_wait();
         float scale = 1.f, shift = 0.f;
-        if (!(p.dbg & 4)) {
+        if (!DFSFM_DBG(p, 4)) {
             // half-row statistics about the first element (no cancellation), then Chan's combination of the two halves
             const float pivot = v[0];
             float s1 = 0.f, s2 = 0.f;
@@ -879,7 +886,7 @@ struct LinEpiS {
     static __device__ __forceinline__ void run(const Params& p, uint32_t tmem_warp, int row0, int lane, int n0, int cb, int ce, int part_idx,
                                                const EpiCtx& ctx) {
         static_assert(kCorr == 0, "engine 2 only");
-        if (p.dbg & 8) return;
+        if (DFSFM_DBG(p, 8)) return;
         if (kMode == LIN_LN) LinEpi::run_ln_staged<BN, kRes>(p, tmem_warp, row0, lane, n0, cb, ctx);
         else LinEpi::run_plain_staged<kMode>(p, tmem_warp, row0, lane, n0, cb, ce, ctx);
     }

@@ -89,28 +89,39 @@ inline CUtensorMap make_tmap(const __half* base, int C, long long rows, long lon
 }
 inline CUtensorMap make_tmap(const HL& b, int box_rows) { return make_tmap(b.hi, b.C, b.rows, b.plane_elems(), box_rows); }
 
+// Function attributes (max dynamic shared memory) and the SM count are PER DEVICE while the C ABI takes a device index per handle:
+// "configured once" state is therefore kept per device ordinal.
+inline int current_device() {
+    int dev = 0;
+    DFSFM_CUDA(cudaGetDevice(&dev));
+    return dev;
+}
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool first() {  // true exactly once per device
+        const int d = current_device() & 63;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 template <int BN, bool kSplit, class Epi>
 inline void launch_gemm(const TmapPack& maps, const GemmCore& core, const typename Epi::Params& ep, int n_total, cudaStream_t st) {
     using Cfg = GemmCfg<BN, kSplit>;
     auto kern = gemm_tc_kernel<BN, kSplit, Epi>;
-    static bool configured = false;
-    if (!configured) {
-        DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     dim3 grid((core.M + kBM - 1) / kBM, (n_total + BN - 1) / BN);
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, core, ep);
     DFSFM_CUDA(cudaGetLastError());
 }
 
 inline int sm_count() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        DFSFM_CUDA(cudaGetDevice(&dev));
-        DFSFM_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
-    return n;
+    static int n[64] = {};
+    const int dev = current_device();
+    if (!n[dev & 63]) DFSFM_CUDA(cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev));
+    return n[dev & 63];
 }
 inline bool pdl_enabled() {
     static int v = -1;
@@ -120,6 +131,7 @@ inline bool pdl_enabled() {
     }
     return v == 1;
 }
+#ifdef DFSFM_LIN_DEBUG  // epilogue ablation switches (tuning builds only: results are wrong by design when set)
 inline int lin_debug_flags() {
     static int v = -1;
     if (v < 0) {
@@ -129,6 +141,7 @@ inline int lin_debug_flags() {
     return v;
 }
 inline void set_debug(LinEpiParams& e) { e.dbg = lin_debug_flags(); }
+#endif
 template <class T>
 inline void set_debug(T&) {}
 // debugging (common.cu): when a timeline capture is armed, the stamp buffer of the next engine-2 launch, else null
@@ -144,11 +157,8 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
             DFSFM_CHECK(core.tap_map[t] == core.tap_map[(t / G) * G] && core.tap_shift[t] == core.tap_shift[(t / G) * G] + t % G,
                         "taps of a group must read the same map at consecutive row shifts");
     }
-    static bool configured = false;
-    if (!configured) {
-        DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-        configured = true;
-    }
+    static PerDeviceOnce once;
+    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     const int m_pairs = (core.M + 2 * kBM - 1) / (2 * kBM);
     const int n_tiles = (n_total + BN - 1) / BN;
     const int tiles = m_pairs * n_tiles;

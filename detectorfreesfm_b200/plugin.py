@@ -57,8 +57,10 @@ def install(coarse=True, refine=True):
             matcher.load_state_dict(torch.load(margs["weight_path"], map_location="cpu")["state_dict"])
             return cmw.DetectorWrapper().eval(), matcher.eval()
         cmw.build_model = build_model
+        cm.build_model = build_model   # coarse_match.py:11 star-imported the original name (match_worker itself resolves it in cmw)
     if refine:
         from omegaconf import OmegaConf
+        from src.post_optimization.matcher_model import multiview_match as mm
         from src.post_optimization.matcher_model import multiview_match_worker as mmw
         from .refine_matcher import B200MultiviewMatcher
 
@@ -72,3 +74,6 @@ def install(coarse=True, refine=True):
                 matcher.load_state_dict({k: v for k, v in sd.items() if "matcher." in k})
             return matcher
         mmw.build_model = build_model
+        # multiview_match.py:7 does ``from .multiview_match_worker import *``: ``multiview_matcher`` (:11) resolves ``build_model`` in
+        # ITS module globals, so the name must be rebound there too or the reference MultiviewMatcher keeps running silently.
+        mm.build_model = build_model

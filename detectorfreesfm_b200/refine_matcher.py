@@ -116,7 +116,7 @@ class B200MultiviewMatcher(torch.nn.Module):
         with torch.cuda.device(dev):
             _lib.check(self._lib.dfsfm_refine_chunk(self._h, n_img, ctypes.cast(ptrs, ctypes.c_void_p), p(Hs), p(Ws), p(scales), M, Nq, p(qpts),
                                                     p(rpts), p(valid), p(q_idx), p(r_idx), p(movable), p(out_q), p(out_r), p(out_s),
-                                                    _lib.stream_ptr()))
+                                                    _lib.stream_ptr(dev)))
         data["W"] = self.W
         data["query_points_refined"] = torch.from_numpy(out_q)[None].to(dev)
         rr = torch.from_numpy(out_r)[None].to(dev)

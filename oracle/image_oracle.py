@@ -110,12 +110,3 @@ def resample_8bpc(img, out_w, out_h):
             out[yy] = np.clip(acc >> PRECISION_BITS, 0, 255)
         cur = out
     return cur
-
-
-def synth_photo(h, w, seed=0):
-    """uint8 test image with smooth structure, edges and noise (full 0..255 range so that the clipping matters)."""
-    rng = np.random.default_rng(seed)
-    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
-    img = 127 + 90 * np.sin(x / 17.0 + seed) * np.cos(y / 23.0) + 60 * ((x // 31 + y // 19) % 2) + rng.normal(0, 25, (h, w))
-    img[: h // 8] = 255 * ((x[: h // 8] // 3) % 2)     # hard 0/255 stripes: overshoot of the negative lobes gets clipped
-    return np.clip(img, 0, 255).astype(np.uint8)

@@ -69,29 +69,3 @@ def merge_keypoints(matches, image_lists, pair_name_split=" "):
             ids[k][:, s] = rank[group[pos:pos + m]]
             pos += m
     return final_kpts, final_scores, ids
-
-
-def synth_matches(n_images, pairs, m_per_pair, hw=(880, 1200), seed=0, grid=8, dup=0.3):
-    """Synthetic matcher output: grid-aligned coordinates (coarse matches sit on the 1/8 grid times a scale), confidences in
-    (0.2, 1], a fraction of repeated key points so that the groupby and the ties matter.  -> (matches dict, names)."""
-    rng = np.random.default_rng(seed)
-    names = [f"/data/scene/img_{i:05d}.jpg" for i in range(n_images)]
-    H, W = hw
-    scale = np.array([1.25, 1.25], dtype=np.float32)
-    matches = {}
-    for (i, j) in pairs:
-        m = int(m_per_pair if np.isscalar(m_per_pair) else m_per_pair[len(matches) % len(m_per_pair)])
-        gx = rng.integers(0, W // grid, size=(m, 2))
-        gy = rng.integers(0, H // grid, size=(m, 2))
-        if dup > 0 and m > 0:
-            # pull a fraction of the points onto a small set of popular cells
-            hot = rng.random(m) < dup
-            gx[hot] = gx[hot] % 7
-            gy[hot] = gy[hot] % 5
-        xy0 = np.stack([gx[:, 0] * grid * scale[0], gy[:, 0] * grid * scale[1]], 1).astype(np.float32)
-        xy1 = np.stack([gx[:, 1] * grid * scale[0], gy[:, 1] * grid * scale[1]], 1).astype(np.float32)
-        conf = (0.2 + 0.8 * rng.random(m)).astype(np.float32)
-        if m > 4:
-            conf[: m // 4] = np.float32(0.5)   # exact ties in the summed scores
-        matches[f"{names[i]} {names[j]}"] = np.concatenate([xy0, xy1, conf[:, None]], 1).astype(np.float32)
-    return matches, names

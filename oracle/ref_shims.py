@@ -62,6 +62,23 @@ def _install_stubs():
 
             def __setattr__(self, k, v):
                 self[k] = v
+
+            def clone(self):
+                import copy
+                return copy.deepcopy(self)
+
+            def _merge(self, other):
+                for k, v in other.items():
+                    if isinstance(v, CfgNode) and isinstance(self.get(k), CfgNode):
+                        self[k]._merge(v)
+                    else:
+                        self[k] = v
+
+            def merge_from_file(self, path):
+                """yacs loads a ``.py`` config by importing it and reading its ``cfg`` (yacs/config.py load_cfg_py_source)"""
+                import runpy
+                assert path.endswith(".py"), path
+                self._merge(runpy.run_path(path)["cfg"])
         _mod("yacs")
         _mod("yacs.config", CfgNode=CfgNode)
     try:
@@ -334,3 +351,59 @@ def import_refine_worker(dataset_cls=None):
     except Exception:
         _mod("omegaconf", OmegaConf=object)
     return importlib.import_module("src.post_optimization.matcher_model.multiview_match_worker")
+
+
+def import_hook_modules():
+    """-> (coarse_match, coarse_match_worker, matcher_model.multiview_match, multiview_match_worker) of the reference, imported
+    where they lie behind inert stubs (ray, h5py, pytorch_lightning, the dataset classes, MultiviewMatcher) so that the two
+    ``build_model`` hooks can be exercised on the CPU box.  yacs / omegaconf are replaced by small
+    work-alikes (``merge_from_file`` of a .py config; ``OmegaConf.load`` = yaml.safe_load) when not installed."""
+    import yaml
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.") or k == "third_party" or k.startswith("third_party.")]:
+        del sys.modules[k]
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    utils = _mod("src.utils")
+    utils.__path__ = [os.path.join(REF, "src", "utils")]
+    _stub_ray()
+    for name in ("h5py",):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            _mod(name)
+    try:
+        import pytorch_lightning  # noqa: F401
+    except Exception:
+        _mod("pytorch_lightning", seed_everything=lambda s: None)
+    om = sys.modules.get("omegaconf")
+    if om is None or not getattr(om, "__file__", None):
+        class OmegaConf:
+            @staticmethod
+            def load(path):
+                with open(path) as f:
+                    return yaml.safe_load(f)
+
+            @staticmethod
+            def to_container(c, **k):
+                return c
+            merge = staticmethod(lambda *cfgs: {k: v for c in cfgs for k, v in dict(c).items()})
+            set_struct = staticmethod(lambda c, v: None)
+            set_readonly = staticmethod(lambda c, v: None)
+        _mod("omegaconf", OmegaConf=OmegaConf)
+    ds = _mod("src.dataset")
+    ds.__path__ = []
+    _mod("src.dataset.coarse_matching_dataset", CoarseMatchingDataset=object)
+    mvm = _mod("src.MultiviewMatcher")
+    mvm.__path__ = []
+    _mod("src.MultiviewMatcher.MultiviewMatcher", MultiviewMatcher=object)
+    po_ = _mod("src.post_optimization")
+    po_.__path__ = [os.path.join(REF, "src", "post_optimization")]
+    _mod("src.post_optimization.data_construct", MatchingMultiviewData=object)
+    cm = importlib.import_module("src.coarse_match.coarse_match")
+    cmw = importlib.import_module("src.coarse_match.coarse_match_worker")
+    mm = importlib.import_module("src.post_optimization.matcher_model.multiview_match")
+    mmw = importlib.import_module("src.post_optimization.matcher_model.multiview_match_worker")
+    return cm, cmw, mm, mmw

@@ -18,7 +18,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from oracle import ref_shims, weights  # noqa: E402
+from oracle import ref_shims  # noqa: E402
+from tests import weights  # noqa: E402
 from tests import util  # noqa: E402
 
 
@@ -118,7 +119,7 @@ def image_golden():
     out = []
     with tempfile.TemporaryDirectory() as d:
         for seed, (h, w, resize, df) in enumerate([(150, 200, (96,), 8), (97, 61, (128,), 8), (64, 80, None, None)]):
-            img = io.synth_photo(h, w, seed)
+            img = util.synth_photo(h, w, seed)
             t, scales, hw = reference_read_grayscale(img, resize, df, d)
             out.append({"image": torch.from_numpy(img), "resize": resize, "df": df, "tensor": t, "scales": scales, "original_hw": hw})
     return out
@@ -139,7 +140,7 @@ def postprocess_golden():
     import itertools
     from oracle import postprocess_oracle as po
     pairs = [p for p in itertools.combinations(range(5), 2) if 4 not in p]  # image 4 never matched
-    matches, names = po.synth_matches(5, pairs, [0, 40, 150], seed=7)
+    matches, names = util.synth_matches(5, pairs, [0, 40, 150], seed=7)
     fk, fs, upd = reference_postprocess(matches, names)
     return {"names": names, "matches": matches, "final_keypoints": fk, "final_scores": fs, "updated_matches": upd}
 

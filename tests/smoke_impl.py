@@ -7,9 +7,9 @@ def run():
     from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher
     from oracle import loftr_oracle as lo
     from oracle import multiview_oracle as mo
-    from oracle import weights
+    from tests import weights
     from tests import util
-    from tests.test_refine_gpu import multiview_config, to_cuda
+    from tests.util import multiview_config, to_cuda
 
     # HP-1: one 96x128 pair through the plugin interface
     sd = weights.loftr_state_dict(0)
@@ -43,7 +43,7 @@ def run():
     import numpy as np
     from detectorfreesfm_b200 import merge_keypoints
     from oracle import postprocess_oracle as po
-    matches, names = po.synth_matches(4, list(itertools.combinations(range(4), 2)), 120, seed=2)
+    matches, names = util.synth_matches(4, list(itertools.combinations(range(4), 2)), 120, seed=2)
     ref_k, ref_s, ref_m = po.merge_keypoints(matches, names, " ")
     out_k, out_s, out_m = merge_keypoints(matches, names, " ")
     for n in names:
@@ -56,7 +56,7 @@ def run():
     from PIL import Image
     from detectorfreesfm_b200 import GpuImageReader
     from oracle import image_oracle as imo
-    photo = imo.synth_photo(300, 400, 1)
+    photo = util.synth_photo(300, 400, 1)
     ref_img = np.asarray(Image.fromarray(photo).resize((160, 120), resample=Image.LANCZOS)).astype("float32") / 255.
     out_img = GpuImageReader().resize_gray(photo, (160, 120)).cpu().numpy()
     assert np.array_equal(out_img, ref_img)

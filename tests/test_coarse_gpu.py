@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import loftr_oracle as lo
-from oracle import weights
+from tests import weights
 from tests import util
 
 pytestmark = pytest.mark.gpu

@@ -3,7 +3,7 @@ these sizes, so the CUDA path is checked against invariants of the algorithm and
 import pytest
 import torch
 
-from oracle import weights
+from tests import weights
 from tests import util
 from tests.test_refine_gpu import multiview_config, to_cuda
 

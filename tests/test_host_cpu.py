@@ -5,6 +5,8 @@ import re
 
 import pytest
 import torch
+
+from tests import util  # noqa: E402
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -65,7 +67,7 @@ def test_unsupported_configs_are_rejected():
 def test_pack_loftr_shapes_and_bn_fold():
     from detectorfreesfm_b200.packing import pack_loftr, position_encoding
     from oracle import loftr_oracle as lo
-    from oracle import weights
+    from tests import weights
     sd = weights.loftr_state_dict(0)
     p = pack_loftr({("matcher." + k): v for k, v in sd.items()})  # checkpoint-style prefix is stripped
     assert p["l2.0.c2.w"][0].shape == (208, 10 * 208) and p["l3.0.c2.w"][0].shape == (256, 10 * 256)
@@ -82,7 +84,7 @@ def test_pack_loftr_shapes_and_bn_fold():
 
 def test_pack_multiview_shapes():
     from detectorfreesfm_b200.packing import pack_multiview
-    from oracle import weights
+    from tests import weights
     p = pack_multiview(weights.multiview_state_dict(0))
     assert p["c11.w"][0].shape == (64, 27) and p["c12.w"][0].shape == (64, 576) and p["c33.w"][0].shape == (256, 2304)
     assert p["a0.2.w"][0].shape == (128, 1600) and p["a1.0.w"][0].shape == (64, 256) and p["tr.3.mlp2"][0].shape == (128, 256)
@@ -122,7 +124,7 @@ def test_partition_and_gather_gloo_world2():
 def test_refinement_window_rescale_matches_reference_rule():
     """multiview_match_worker.py:20-34: window 15 -> 11 -> 7 (floor 7), left window 7 -> 3 (floor 3) per refinement iteration."""
     from detectorfreesfm_b200.plugin import rescale_windows
-    from tests.test_refine_gpu import multiview_config
+    from tests.util import multiview_config
     cfg = multiview_config(15, 7)
     got = []
     for factor in (None, 0, 2, 4, 6):
@@ -191,7 +193,7 @@ def _post_worker(rank, world, port, q):
     from oracle import postprocess_oracle as po
     r, w, _ = D.init_from_env(backend="gloo")
     pairs = [p for p in itertools.combinations(range(6), 2) if 5 not in p]       # image 5 never matched
-    matches, names = po.synth_matches(6, pairs, [0, 30, 120], seed=3, dup=0.4)
+    matches, names = util.synth_matches(6, pairs, [0, 30, 120], seed=3, dup=0.4)
     keys = list(matches.keys())
     mine = D.shard(len(keys), r, w)                                               # strided, as the HP-1 bench shards pairs
     local = {keys[i]: matches[keys[i]] for i in mine}
@@ -226,7 +228,7 @@ def test_sharded_postprocess_single_process_path():
     import numpy as np
     from detectorfreesfm_b200.postprocess_dist import image_owner, merge_keypoints_sharded
     from oracle import postprocess_oracle as po
-    matches, names = po.synth_matches(4, list(itertools.combinations(range(4), 2)), 60, seed=9)
+    matches, names = util.synth_matches(4, list(itertools.combinations(range(4), 2)), 60, seed=9)
     fk, fs, upd = merge_keypoints_sharded(matches, list(range(len(matches))), names, " ", local_merge=_oracle_flat_merge)
     ref = po.merge_keypoints(matches, names, " ")
     assert all(np.array_equal(fk[n], ref[0][n]) and np.array_equal(fs[n], ref[1][n]) for n in names)

@@ -7,6 +7,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests import util  # noqa: E402
+
 from oracle import image_oracle as io
 
 pytestmark = pytest.mark.gpu
@@ -23,7 +25,7 @@ def reader():
                                        (17, 17, 17, 17), (5, 7, 1, 1), (200, 300, 208, 304), (3000, 4000, 624, 832), (880, 1200, 880, 1200)])
 def test_resize_matches_pil(reader, H, W, oh, ow):
     from PIL import Image
-    img = io.synth_photo(H, W, seed=H + W)
+    img = util.synth_photo(H, W, seed=H + W)
     ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.LANCZOS)).astype("float32") / 255.
     out = reader.resize_gray(img, (ow, oh)).cpu().numpy()
     assert out.shape == ref.shape and out.dtype == np.float32
@@ -36,7 +38,7 @@ def test_resize_matches_pil(reader, H, W, oh, ow):
 def test_read_grayscale_matches_oracle_and_golden(reader, tmp_path):
     import cv2
     for seed, (h, w, resize, df) in enumerate([(150, 200, (96,), 8), (97, 61, (128,), 8), (64, 80, None, None), (300, 200, (64, 48), None)]):
-        img = io.synth_photo(h, w, seed)
+        img = util.synth_photo(h, w, seed)
         path = str(tmp_path / f"im{seed}.png")
         assert cv2.imwrite(path, img)
         t, s, hw = reader.read_grayscale(path, resize, df=df, ret_scales=True)
@@ -48,7 +50,7 @@ def test_read_grayscale_matches_oracle_and_golden(reader, tmp_path):
         t, s, hw = reader.read_grayscale(path, g["resize"], df=g["df"], ret_scales=True)
         assert torch.equal(t.cpu(), g["tensor"]) and torch.equal(s, g["scales"]) and torch.equal(hw, g["original_hw"])
     # pad_to: zeros to the bottom / right, mask of the valid area (utils.py:33-52)
-    img = io.synth_photo(90, 120, 5)
+    img = util.synth_photo(90, 120, 5)
     path = str(tmp_path / "pad.png")
     cv2.imwrite(path, img)
     t, s, hw, mask = reader.read_grayscale(path, (64,), df=8, pad_to=-1, ret_scales=True, ret_pad_mask=True)
@@ -65,7 +67,7 @@ def test_dataset_mirror_caches_and_feeds_the_matcher(tmp_path):
     paths = []
     imgs = []
     for i in range(3):
-        img = io.synth_photo(120 + 8 * i, 160, 10 + i)
+        img = util.synth_photo(120 + 8 * i, 160, 10 + i)
         p = str(tmp_path / f"scene_{i}.png")
         cv2.imwrite(p, img)
         paths.append(p)

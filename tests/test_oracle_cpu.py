@@ -7,7 +7,7 @@ import torch
 from oracle import build_native
 from oracle import loftr_oracle as lo
 from oracle import multiview_oracle as mo
-from oracle import weights
+from tests import weights
 from tests import util
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -115,7 +115,7 @@ def test_image_oracle_vs_golden_and_pillow_restatement():
         assert torch.equal(t, g["tensor"]) and torch.equal(s, g["scales"]) and torch.equal(hw, g["original_hw"])
     for (H, W, oh, ow) in [(120, 160, 90, 120), (100, 37, 64, 24), (33, 50, 99, 120), (64, 64, 64, 32), (17, 17, 17, 17), (5, 7, 1, 1),
                            (700, 900, 208, 264)]:
-        img = io.synth_photo(H, W, seed=H + W)
+        img = util.synth_photo(H, W, seed=H + W)
         ref = np.asarray(Image.fromarray(img).resize((ow, oh), resample=Image.LANCZOS))
         assert np.array_equal(ref, io.resample_8bpc(img, ow, oh)), (H, W, oh, ow)
 

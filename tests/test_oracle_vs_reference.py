@@ -3,6 +3,8 @@ only; skipped on the GPU box where that tree does not exist -- the committed gol
 import pytest
 import torch
 
+from tests import util  # noqa: E402
+
 from oracle import ref_shims
 
 pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="/root/reference not present")
@@ -10,7 +12,7 @@ pytestmark = pytest.mark.skipif(not ref_shims.available(), reason="/root/referen
 
 def test_loftr_coarse_and_fine_match_reference():
     from oracle import loftr_oracle as lo
-    from oracle import weights
+    from tests import weights
     from tests import util
     LoFTR, _ = ref_shims.import_loftr()
     sd = weights.loftr_state_dict(0)
@@ -32,7 +34,7 @@ def test_loftr_coarse_and_fine_match_reference():
 
 def test_multiview_matches_reference():
     from oracle import multiview_oracle as mo
-    from oracle import weights
+    from tests import weights
     from tests import util
     MM = ref_shims.import_multiview()
     sd = weights.multiview_state_dict(0)
@@ -73,7 +75,7 @@ def test_postprocess_oracle_matches_reference():
         pairs = list(itertools.combinations(range(n), 2))
         if seed == 2:
             pairs = [p for p in pairs if 4 not in p]
-        matches, names = po.synth_matches(n, pairs, m, seed=seed)
+        matches, names = util.synth_matches(n, pairs, m, seed=seed)
         ref = reference_postprocess(matches, names)
         ora = po.merge_keypoints(matches, names, " ")
         for name in names:
@@ -88,7 +90,7 @@ def test_image_oracle_matches_reference_read_grayscale(tmp_path):
     from oracle import image_oracle as io
     from tests.golden.make_golden import reference_read_grayscale
     for seed, (h, w, resize, df) in enumerate([(150, 200, (96,), 8), (97, 61, (128,), 8), (64, 80, None, None), (300, 200, (64, 48), None)]):
-        img = io.synth_photo(h, w, seed)
+        img = util.synth_photo(h, w, seed)
         t, scales, hw = reference_read_grayscale(img, resize, df, str(tmp_path))
         to, so, ho = io.read_grayscale_from_array(img, resize, df=df)
         assert t.dtype == to.dtype and torch.equal(t, to) and torch.equal(scales, so) and torch.equal(hw, ho)
@@ -108,3 +110,48 @@ def test_refine_worker_loop_matches_reference_match_worker():
     assert len(ref) == len(got) == 3
     for a, b in zip(ref, got):
         assert a.shape == b.shape and a.shape[1] == 4 and np.array_equal(a, b)
+
+
+def test_plugin_install_rebinds_both_hooks_and_builds_b200_models(tmp_path, monkeypatch):
+    """plugin.install() behind the reference's own hook modules (imported where they lie, third-party deps stubbed):
+    * the HP-1 name 'loftr_b200' builds (DetectorWrapper, B200LoFTR) from the reference's yacs config + a checkpoint file, with
+      thr / temp_bug_fix overwritten like coarse_match_worker.py:31-35, and other matcher names still reach the original;
+    * the HP-2 builder is rebound in BOTH modules that hold the name (multiview_match.py star-imports it, :7) and applies the
+      per-iteration window rescale of multiview_match_worker.py:20-34."""
+    import os
+    from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher
+    from detectorfreesfm_b200 import plugin
+    from tests import weights
+    cm, cmw, mm, mmw = ref_shims.import_hook_modules()
+    orig_coarse, orig_refine = cmw.build_model, mmw.build_model
+    assert mm.build_model is orig_refine                      # the star import the advisor pointed at
+    plugin.install()
+    assert cmw.build_model is not orig_coarse and cm.build_model is cmw.build_model
+    assert mmw.build_model is not orig_refine and mm.build_model is mmw.build_model
+    assert "loftr_b200" in cm.cfgs["matcher"]["model"]
+    # ---- HP-1
+    ckpt = tmp_path / "outdoor_ds.ckpt"
+    torch.save({"state_dict": {"matcher." + k: v for k, v in weights.loftr_state_dict(0).items()}}, ckpt)
+    monkeypatch.chdir(ref_shims.REF)                          # the yacs .py configs use cwd-relative paths, like eval_dataset.py
+    args = dict(cm.cfgs["matcher"]["model"])
+    args.update({"matcher": "loftr_b200", "type": "coarse_only", "match_thr": 0.35})
+    args["loftr_b200"] = {**args["loftr_b200"], "weight_path": str(ckpt)}
+    detector, matcher = cmw.build_model(args)
+    assert isinstance(detector, cmw.DetectorWrapper) and isinstance(matcher, B200LoFTR)
+    assert matcher.thr == 0.35 and matcher.fine is False and matcher.temperature == 0.1 and matcher._packed is not None
+    args["type"] = "coarse_fine"
+    _, matcher_f = cmw.build_model(args)
+    assert matcher_f.fine is True
+    with pytest.raises(NotImplementedError):                  # unknown names still fall through to the reference's if/elif chain
+        cmw.build_model({**args, "matcher": "no_such_matcher", "seed": 0})
+    # ---- HP-2
+    ckpt2 = tmp_path / "multiview_matcher.ckpt"
+    sdm = {"matcher." + k.replace("fine_transformer", "loftr_fine"): v for k, v in weights.multiview_state_dict(0).items()}
+    sdm["matcher.loftr_coarse.layers.0.q_proj.weight"] = torch.zeros(4, 4)   # dropped by the reference (:47-49) and by the packer
+    sdm["loss.whatever"] = torch.zeros(1)
+    torch.save({"state_dict": sdm}, ckpt2)
+    yaml_path = os.path.join(ref_shims.REF, "hydra_training_configs", "experiment", "multiview_refinement_matching.yaml")
+    margs = {"cfg_path": [yaml_path], "weight_path": [str(ckpt2)], "seed": 666}
+    for factor, (w, lw) in {None: (15, 7), 1: (13, 5), 2: (11, 3), 5: (7, 3)}.items():
+        m = mm.build_model(margs, rewindow_size_factor=factor, model_idx=0)
+        assert isinstance(m, B200MultiviewMatcher) and (m.W, m.LW) == (w, lw) and m._packed is not None

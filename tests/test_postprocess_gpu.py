@@ -8,6 +8,8 @@ import numpy as np
 import pytest
 import torch
 
+from tests import util  # noqa: E402
+
 from oracle import postprocess_oracle as po
 
 pytestmark = pytest.mark.gpu
@@ -35,7 +37,7 @@ def test_merge_keypoints_matches_oracle(case):
     pairs = list(itertools.combinations(range(n), 2))
     if case == 2:
         pairs = [p for p in pairs if 4 not in p]          # image 4 never matched; some pairs empty
-    matches, names = po.synth_matches(n, pairs, m, seed=case, dup=dup)
+    matches, names = util.synth_matches(n, pairs, m, seed=case, dup=dup)
     ref = po.merge_keypoints(matches, names, " ")
     mg = _merger()
     _assert_equal(mg(matches, names, " "), ref, names, matches.keys())
@@ -74,7 +76,7 @@ def test_large_properties():
     """64 images, all 2016 pairs, ~1000 matches each (4 M observations): size-independent properties instead of the oracle."""
     n = 64
     pairs = list(itertools.combinations(range(n), 2))
-    matches, names = po.synth_matches(n, pairs, 1000, seed=11, dup=0.25)
+    matches, names = util.synth_matches(n, pairs, 1000, seed=11, dup=0.25)
     fk, fs, upd = _merger()(matches, names, " ")
     index = {nm: i for i, nm in enumerate(names)}
     total_conf = 0.0

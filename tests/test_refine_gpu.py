@@ -5,32 +5,13 @@ import torch
 
 from oracle import build_native
 from oracle import multiview_oracle as mo
-from oracle import weights
+from tests import weights
 from tests import util
 
 pytestmark = pytest.mark.gpu
 
 
-def multiview_config(window=15, left_window=7):
-    mm = {"enable": True, "type": "s2d", "detector": "OnGrid", "window_size": window, "best_left_strategy": "smallest_mean_std",
-          "s2d": {"type": "heatmap", "obtain_offset_method": "argsoftmax"}}
-    return {"n_matching_steps": 1, "enable_multiview_scale_align": False,
-            "backbone": {"type": "S2DNet", "resolution": [4, 1], "s2dnet": {"window_size": window}, "pretrained": None},
-            "multiview_transform": {"sparse": True, "crop_size": 35, "window_size": window, "enable": True, "type": "LoFTR", "d_model": 128,
-                                    "nhead": 8, "layer_names": ["self", "cross"], "layer_iter_n": 2, "attention": "linear"},
-            "multiview_matching_test": {**mm, "left_point_movement_window_size": left_window}}
-
-
-def to_cuda(data):
-    out = {}
-    for k, v in data.items():
-        if isinstance(v, list):
-            out[k] = [x.cuda() for x in v]
-        elif torch.is_tensor(v):
-            out[k] = v.cuda()
-        else:
-            out[k] = v
-    return out
+multiview_config, to_cuda = util.multiview_config, util.to_cuda   # shared with bench.py / smoke (generators live in tests/util.py)
 
 
 def test_crop_and_resize_matches_oracle(lib):

@@ -14,7 +14,7 @@ def test_coarse_matching_stage_matches_oracle_chain(tmp_path):
     from oracle import image_oracle as io
     from oracle import loftr_oracle as lo
     from oracle import postprocess_oracle as po
-    from oracle import weights
+    from tests import weights
     from tests import util
 
     # three views of the same synthetic texture, written as PNGs larger than the matching resolution

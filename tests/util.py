@@ -1,4 +1,5 @@
 """Seeded synthetic inputs shared by tests, smoke() and bench.py."""
+import numpy as np
 import torch
 
 
@@ -114,3 +115,77 @@ class StandInRefiner:
     def __call__(self, data):
         data["query_points_refined"] = data["query_points"] + 0.25
         data["reference_points_refined"] = [data["reference_points_coarse"] * 0 + 1.0, data["reference_points_coarse"] - 0.5]
+
+
+def synth_matches(n_images, pairs, m_per_pair, hw=(880, 1200), seed=0, grid=8, dup=0.3):
+    """Synthetic matcher output: grid-aligned coordinates (coarse matches sit on the 1/8 grid times a scale), confidences in
+    (0.2, 1], a fraction of repeated key points so that the groupby and the ties matter.  -> (matches dict, names)."""
+    rng = np.random.default_rng(seed)
+    names = [f"/data/scene/img_{i:05d}.jpg" for i in range(n_images)]
+    H, W = hw
+    scale = np.array([1.25, 1.25], dtype=np.float32)
+    matches = {}
+    for (i, j) in pairs:
+        m = int(m_per_pair if np.isscalar(m_per_pair) else m_per_pair[len(matches) % len(m_per_pair)])
+        gx = rng.integers(0, W // grid, size=(m, 2))
+        gy = rng.integers(0, H // grid, size=(m, 2))
+        if dup > 0 and m > 0:
+            # pull a fraction of the points onto a small set of popular cells
+            hot = rng.random(m) < dup
+            gx[hot] = gx[hot] % 7
+            gy[hot] = gy[hot] % 5
+        xy0 = np.stack([gx[:, 0] * grid * scale[0], gy[:, 0] * grid * scale[1]], 1).astype(np.float32)
+        xy1 = np.stack([gx[:, 1] * grid * scale[0], gy[:, 1] * grid * scale[1]], 1).astype(np.float32)
+        conf = (0.2 + 0.8 * rng.random(m)).astype(np.float32)
+        if m > 4:
+            conf[: m // 4] = np.float32(0.5)   # exact ties in the summed scores
+        matches[f"{names[i]} {names[j]}"] = np.concatenate([xy0, xy1, conf[:, None]], 1).astype(np.float32)
+    return matches, names
+
+
+def synth_photo(h, w, seed=0):
+    """uint8 test image with smooth structure, edges and noise (full 0..255 range so that the clipping matters)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w].astype(np.float64)
+    img = 127 + 90 * np.sin(x / 17.0 + seed) * np.cos(y / 23.0) + 60 * ((x // 31 + y // 19) % 2) + rng.normal(0, 25, (h, w))
+    img[: h // 8] = 255 * ((x[: h // 8] // 3) % 2)     # hard 0/255 stripes: overshoot of the negative lobes gets clipped
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def synth_scene(n_images, h, w, seed, noise=0.025, max_shift=256, align=8):
+    """An overlapping-view scene: ``n_images`` crops [1,1,h,w] of one big low-pass noise image at seeded offsets that are
+    multiples of ``align`` px (views related by translation, coarse cells aligned), plus independent per-view Gaussian
+    noise -- with the BN-calibrated synthetic weights (tests/weights.py) every pair yields O(10^3) mutual-NN matches with
+    confidences spread over (0.2, 1], like a real scene.  Returns (images, offsets[(dy, dx)])."""
+    g = torch.Generator().manual_seed(seed)
+    base = synth_image(h + max_shift, w + max_shift, seed)
+    n_off = max_shift // align + 1
+    offs = [(0, 0)] + [(int(torch.randint(0, n_off, (1,), generator=g)) * align, int(torch.randint(0, n_off, (1,), generator=g)) * align)
+                       for _ in range(n_images - 1)]
+    images = []
+    for dy, dx in offs:
+        crop = base[:, :, dy:dy + h, dx:dx + w]
+        images.append((crop + noise * torch.randn(crop.shape, generator=g)).clamp(0, 1).contiguous())
+    return images, offs
+
+
+def multiview_config(window=15, left_window=7):
+    mm = {"enable": True, "type": "s2d", "detector": "OnGrid", "window_size": window, "best_left_strategy": "smallest_mean_std",
+          "s2d": {"type": "heatmap", "obtain_offset_method": "argsoftmax"}}
+    return {"n_matching_steps": 1, "enable_multiview_scale_align": False,
+            "backbone": {"type": "S2DNet", "resolution": [4, 1], "s2dnet": {"window_size": window}, "pretrained": None},
+            "multiview_transform": {"sparse": True, "crop_size": 35, "window_size": window, "enable": True, "type": "LoFTR", "d_model": 128,
+                                    "nhead": 8, "layer_names": ["self", "cross"], "layer_iter_n": 2, "attention": "linear"},
+            "multiview_matching_test": {**mm, "left_point_movement_window_size": left_window}}
+
+
+def to_cuda(data):
+    out = {}
+    for k, v in data.items():
+        if isinstance(v, list):
+            out[k] = [x.cuda() for x in v]
+        elif torch.is_tensor(v):
+            out[k] = v.cuda()
+        else:
+            out[k] = v
+    return out

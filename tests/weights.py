@@ -6,8 +6,16 @@ BatchNorm gets non-trivial running stats / affine terms (so that BN folding is t
 and biased layers get non-zero biases.
 
 Shapes: SURVEY.md appendix B (read off the instantiated reference modules).
+
+``loftr_state_dict(seed, calibrated=True)`` additionally sets every backbone BatchNorm's running statistics to the
+statistics of its own input on a seeded calibration image -- what training does to a real checkpoint.  With arbitrary
+running stats a random ReLU network collapses onto a handful of directions (participation ratio of the 1/8 features
+~4 of 256) and the dual-softmax never exceeds 1e-3; with data-matched statistics the features stay high-dimensional
+(~110) and the default thr 0.2 / temperature 0.1 yields thousands of mutual-NN matches on overlapping views, like the
+real model.  Pure generator code (plain torch ops, no oracle import): bench.py's product arm uses it.
 """
 import torch
+import torch.nn.functional as F
 
 
 def _conv_w(g, cout, cin, k, gain=2.0):
@@ -40,8 +48,43 @@ def _encoder(g, sd, p, d):
         sd[f"{p}.{n}.bias"] = 0.1 * torch.randn(d, generator=g)
 
 
-def loftr_state_dict(seed=0):
+def calibrate_backbone_bn(sd, image, p="backbone"):
+    """Returns a copy of ``sd`` whose ResNetFPN_8_2 BatchNorms (coarse sub-graph, resnet_fpn.py:100-108) carry the
+    per-channel mean / biased variance of their own inputs on ``image`` [1,1,H,W], computed layer by layer."""
+    sd = dict(sd)
+
+    def bn(x, name):
+        sd[name + ".running_mean"] = x.mean((0, 2, 3))
+        sd[name + ".running_var"] = x.var((0, 2, 3), unbiased=False)
+        return F.batch_norm(x, sd[name + ".running_mean"], sd[name + ".running_var"], sd[name + ".weight"], sd[name + ".bias"], False, 0.0, 1e-5)
+
+    def block(x, q, stride):
+        y = F.relu(bn(F.conv2d(x, sd[q + ".conv1.weight"], None, stride, 1), q + ".bn1"))
+        y = bn(F.conv2d(y, sd[q + ".conv2.weight"], None, 1, 1), q + ".bn2")
+        if stride != 1:
+            x = bn(F.conv2d(x, sd[q + ".downsample.0.weight"], None, stride, 0), q + ".downsample.1")
+        return F.relu(x + y)
+
+    x = F.relu(bn(F.conv2d(image, sd[p + ".conv1.weight"], None, 2, 3), p + ".bn1"))
+    for li, stride in ((1, 1), (2, 2), (3, 2)):
+        x = block(x, f"{p}.layer{li}.0", stride)
+        x = block(x, f"{p}.layer{li}.1", 1)
+    return sd
+
+
+_CAL_CACHE = {}
+
+
+def loftr_state_dict(seed=0, calibrated=False):
     """LoFTR (outdoor_ds layout): third_party/LoFTR/src/loftr/loftr.py:12-27."""
+    if calibrated:
+        if seed not in _CAL_CACHE:
+            g = torch.Generator().manual_seed(1000 + seed)
+            cal = F.avg_pool2d(torch.rand(1, 1, 260, 260, generator=g), 5, 1)
+            cal = (cal - cal.min()) / (cal.max() - cal.min())
+            with torch.no_grad():
+                _CAL_CACHE[seed] = calibrate_backbone_bn(loftr_state_dict(seed), cal)
+        return dict(_CAL_CACHE[seed])
     g = torch.Generator().manual_seed(seed)
     sd = {}
     dims = [128, 196, 256]

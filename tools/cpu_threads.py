@@ -1,7 +1,8 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import loftr_oracle as lo, weights
+from oracle import loftr_oracle as lo
+from tests import weights
 from tests import util
 sd = weights.loftr_state_dict(0)
 im0, im1 = util.synth_image(832, 832, 1000), util.synth_image(832, 832, 1001)

@@ -4,19 +4,20 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher
-from oracle import weights
+from tests import weights
 from tests import util
-from tests.test_refine_gpu import multiview_config, to_cuda
+from tests.util import multiview_config, to_cuda
 
 n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 tracks = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 m = B200LoFTR(util.loftr_config()).cuda().eval()
-m.load_state_dict(weights.loftr_state_dict(0))
-ims = [util.synth_image(832, 832, 1000 + i).cuda() for i in range(2)]
+m.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
+ims = [im.cuda() for im in util.synth_scene(2, 832, 832, 1000, noise=0.025)[0]]
 for _ in range(n_pairs):
     d = {"image0": ims[0], "image1": ims[1]}
     m(d)
 torch.cuda.synchronize()
+print("matches", len(d["mconf"]))
 if tracks:
     rm = B200MultiviewMatcher(multiview_config(15, 7), test=True).cuda().eval()
     rm.load_state_dict(weights.multiview_state_dict(0))

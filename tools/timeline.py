@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from detectorfreesfm_b200 import B200LoFTR, _lib
-from oracle import weights
+from tests import weights
 from tests import util
 
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
