@@ -1,6 +1,7 @@
 // HP-1: pairwise coarse matcher (LoFTR coarse_only path) on the B200 -- layer schedule and C ABI.
 // Reference: third_party/LoFTR/src/loftr/loftr.py:29-73 (stage order), backbone/resnet_fpn.py:100-108 (coarse sub-graph),
 // loftr_module/transformer.py:35-101, utils/coarse_matching.py:84-258.
+#include <algorithm>
 #include <map>
 #include <memory>
 
@@ -61,6 +62,11 @@ struct TokWs {  // transformer / matcher workspace for up to `cap` tokens per si
     HL x[2], msg[2], m1[2], hid[2];
     float* qkv[2] = {nullptr, nullptr};
     float* xf = nullptr;       // joint fp32 token array (residual stream)
+    HL g;                      // [2 segments * 256][256] per-call folded attention-state x merge matrices (attn_fold_merge_kernel)
+    float* ksum = nullptr;     // [2][256]
+    float* kvp_part = nullptr;   // KvEpi per-CTA partial states [2 segments][2 column tiles][CTAs][4*32*33]
+    unsigned* kvp_flags = nullptr;
+    int L = 0, L1 = 0, S = 0;  // layout of the joint token array of the current transformer() call
     int kv_chunks = 0;
     float* kv_part = nullptr;
     float* kv_state = nullptr;
@@ -95,6 +101,7 @@ class CoarseEngine {
     int device_;
     std::map<std::pair<int, int>, FeatWs> feat_ws_;
     TokWs tok_;
+    unsigned kv_epoch_ = 0;
     FineWs fine_;
     void ensure_fine(int M);
     void fine_branch(FeatWs& w, float* feat_f, cudaStream_t st);
@@ -107,7 +114,8 @@ class CoarseEngine {
 
     template <int BN>
     void conv(const HL* ins, int n_in, GemmCore core, const std::string& wname, ConvEpiParams ep, cudaStream_t st);
-    void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st);
+    void layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count, cudaStream_t st,
+                    int seg_row0 = 0);
 };
 
 static int kv_tok() {  // tokens per KV-partial CTA (A/B: DFSFM_KV_TOK)
@@ -118,6 +126,24 @@ static int kv_tok() {  // tokens per KV-partial CTA (A/B: DFSFM_KV_TOK)
         if (v < 16) v = 16;
     }
     return v;
+}
+// DFSFM_ATTN_FOLD=0: the round-1 schedule (fp32 q/k/v, attn_apply kernel, merge on the message) as an A/B reference.
+static bool attn_fold() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_ATTN_FOLD");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1 && engine_version() == 2;
+}
+// DFSFM_KV_EPI=0: k/v written as fp32 and reduced by kv_partial/kv_final (A/B reference for the fused-epilogue state reduction)
+static bool kv_epi() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_KV_EPI");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
 }
 static bool lin_bn128() {  // A/B switch: 128-wide N tiles for the wide linears (QKV, KV, mlp.0): twice the tiles, better last-round fill
     static int v = -1;
@@ -355,6 +381,11 @@ void CoarseEngine::free_tok(TokWs& w) {
     }
     if (w.xf) cudaFree(w.xf);
     w.xf = nullptr;
+    hl_free(w.g);
+    if (w.ksum) cudaFree(w.ksum);
+    if (w.kvp_part) cudaFree(w.kvp_part);
+    if (w.kvp_flags) cudaFree(w.kvp_flags);
+    w.ksum = nullptr; w.kvp_part = nullptr; w.kvp_flags = nullptr;
     if (w.kv_part) cudaFree(w.kv_part);
     if (w.kv_state) cudaFree(w.kv_state);
     if (w.seg_dev) cudaFree(w.seg_dev);
@@ -378,6 +409,11 @@ void CoarseEngine::ensure_tok(int n) {
     }
     tok_.kv_chunks = (cap + kv_tok() - 1) / kv_tok();
     DFSFM_CUDA(cudaMalloc(&tok_.xf, static_cast<size_t>(cap) * 256 * sizeof(float)));
+    tok_.g = hl_alloc(512, 256);
+    DFSFM_CUDA(cudaMalloc(&tok_.ksum, 512 * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.kvp_part, static_cast<size_t>(4) * sm_count() * kKvPartFloats * sizeof(float)));
+    DFSFM_CUDA(cudaMalloc(&tok_.kvp_flags, static_cast<size_t>(4) * sm_count() * sizeof(unsigned)));
+    DFSFM_CUDA(cudaMemset(tok_.kvp_flags, 0, static_cast<size_t>(4) * sm_count() * sizeof(unsigned)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(2) * tok_.kv_chunks * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(2) * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 8 * sizeof(Seg)));
@@ -399,7 +435,7 @@ static bool res_hl() {
 }
 
 void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn, int kv_seg0, int n_segs, int apply_seg0, int max_count,
-                              cudaStream_t st) {
+                              cudaStream_t st, int seg_row0) {
     const std::string p = "tr." + std::to_string(li);
     GemmCore c;
     memset(&c, 0, sizeof(c));
@@ -409,8 +445,88 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     float* qkv = tok_.qkv[0];
     float* xf = tok_.xf;
     auto rows_map = [&](const HL& b, int r0, int n) { return make_tmap(b.hi + static_cast<long long>(r0) * b.C, b.C, n, b.plane_elems(), kBM); };
+    const bool fold = attn_fold();
+    if (fold && kv_epi()) {
+        // (1+2) k, v projection of the source rows with the linear-attention state reduced in the GEMM epilogue (KvEpi)
+        TmapPack maps;
+        maps.b = make_tmap(params.mat(p + ".kvp"), bbox(256));
+        for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], s0, sn);
+        KvEpiParams ke;
+        memset(&ke, 0, sizeof(ke));
+        ke.M = sn;
+        ke.seg_row0 = seg_row0;
+        if (seg_row0 > 0) {  // both images: rows [0,L) and [L1, L1+S)
+            ke.row_begin[0] = 0; ke.row_end[0] = tok_.L; ke.row_begin[1] = tok_.L1; ke.row_end[1] = tok_.L1 + tok_.S;
+        } else {
+            ke.row_begin[0] = 0; ke.row_end[0] = sn;
+        }
+        ke.part = tok_.kvp_part; ke.flags = tok_.kvp_flags; ke.epoch = ++kv_epoch_;
+        c.M = sn; c.b_row0 = 0;
+        const int tiles = ((sn + 2 * kBM - 1) / (2 * kBM)) * 2;
+        const int n_ctas = 2 * std::min(tiles, sm_count() / 2);
+        { LaunchScope ls("kvproj", st);
+          launch_gemm2<256, true, KvEpi>(maps, c, ke, 512, st); }
+        { LaunchScope ls("kv_final", st);
+          kv_state_final_kernel<<<dim3((8 * 32 * 33 + 63) / 64, n_segs), 256, 0, st>>>(tok_.kvp_part, tok_.kvp_flags, ke.epoch, n_ctas, kKvPartFloats,
+                                                                                    tok_.seg_dev + kv_seg0, tok_.kv_state); }
+        DFSFM_CUDA(cudaGetLastError());
+    }
+    if (fold && !kv_epi()) {
+        // (1) k, v of the source rows (elu+1 on k) -> fp32 for the state reduction
+        {
+            TmapPack maps;
+            maps.b = make_tmap(params.mat(p + ".qkv"), bbox(256));
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], s0, sn);
+            memset(&e, 0, sizeof(e));
+            e.mode = LIN_F32_ELU; e.out_f32_ld = 768;
+            c.M = sn; c.b_row0 = 256;
+            e.M = sn; e.N = 512; e.elu_cols = 256; e.out_f32 = qkv + static_cast<long long>(s0) * 768; e.out_col0 = 256;
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
+        }
+        // (2) KV state(s) of the source segment(s)
+        const int chunks = (max_count + kv_tok() - 1) / kv_tok();
+        { LaunchScope ls("kv", st);
+          kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
+                                                                      kv_tok()); }
+        { LaunchScope ls("kv_final", st);
+          kv_final_kernel<32><<<dim3((256 * 33 + 63) / 64, n_segs), kKvFinalThreads, 0, st>>>(tok_.kv_part, tok_.seg_dev + kv_seg0, tok_.kv_chunks,
+                                                                                   tok_.kv_state, kv_tok()); }
+    }
+    if (fold) {
+        // (3) fold the state into the merge projection: G = len * KV . Wm^T per segment, Ksum as a dense vector
+        { const HL& wm = params.mat(p + ".merge");
+          LaunchScope ls("fold", st);
+          attn_fold_merge_kernel<32><<<dim3(8, n_segs), 256, 0, st>>>(tok_.kv_state, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(), tok_.g.hi, tok_.g.lo(),
+                                                                  tok_.ksum); }
+        DFSFM_CUDA(cudaGetLastError());
+        // (4) q of the attending rows with the normaliser folded in: Q*Z -> split planes (the msg buffer)
+        {
+            TmapPack maps;
+            maps.b = make_tmap(params.mat(p + ".qkv"), bbox(256));
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
+            memset(&e, 0, sizeof(e));
+            e.mode = LIN_QZ; e.ksum = tok_.ksum; e.seg_row0 = seg_row0;
+            c.M = xn; c.b_row0 = 0;
+            e.M = xn; e.N = 256;
+            e.out_hi = tok_.msg[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.msg[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
+            launch_gemm_counted<256, true, LinEpi>(maps, c, e, 256, st, "lin");
+        }
+        // (5) attention + merge + norm1 in one GEMM against the folded matrix of the row's segment
+        {
+            TmapPack maps;
+            for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.msg[0], x0, xn);
+            maps.b = make_tmap(tok_.g, bbox(256));
+            GemmCore cg = c;
+            cg.seg_mp0 = seg_row0 / (2 * kBM); cg.seg_b_rows = 256;
+            memset(&e, 0, sizeof(e));
+            e.M = xn; e.N = 256; e.mode = LIN_LN;
+            e.gamma = params.vec(p + ".ln1.g"); e.beta = params.vec(p + ".ln1.b");
+            e.out_hi = tok_.m1[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.m1[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;
+            launch_gemm_counted<256, true, LinEpi>(maps, cg, e, 256, st, "lin");
+        }
+    }
     // q/k/v projections (+ elu+1 feature map on q,k)
-    {
+    if (!fold) {
         TmapPack maps;
         maps.b = make_tmap(params.mat(p + ".qkv"), bbox(256));
         memset(&e, 0, sizeof(e));
@@ -437,7 +553,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             else launch_gemm_counted<256, true, LinEpi>(maps, c, e, 512, st, "lin");
         }
     }
-    {   // KV state(s): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
+    if (!fold) {   // KV state(s): K = qkv[:,256:512] (already elu+1), V = qkv[:,512:768]
         const int chunks = (max_count + kv_tok() - 1) / kv_tok();
         { LaunchScope ls("kv", st);
           kv_partial_kernel<32><<<dim3(chunks, n_segs), 256, 0, st>>>(qkv + 256, qkv + 512, 768, tok_.seg_dev + kv_seg0, tok_.kv_chunks, tok_.kv_part,
@@ -452,7 +568,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     }
     c.M = xn; c.b_row0 = 0;
     // merge + norm1
-    {
+    if (!fold) {
         TmapPack maps;
         for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.msg[0], x0, xn);
         maps.b = make_tmap(params.mat(p + ".merge"), bbox(256));
@@ -507,25 +623,32 @@ static void split_rows(const float* in, long long rows, int C, __half* hi, __hal
 }
 
 void CoarseEngine::transformer(float* f0, int L, float* f1, int S, cudaStream_t st) {
-    ensure_tok(L + S);
-    // joint token array: image 0 rows [0,L), image 1 rows [L,L+S); attention segments / KV-state slots:
+    // joint token array: image 0 rows [0,L), image 1 rows [L1,L1+S).  With the folded schedule image 1 starts on a 256-row tile
+    // boundary (rows [L,L1) are zero padding that no attention segment covers), so that every row tile of a launch over both
+    // images belongs to ONE image and can pick that image's folded merge matrix.  Attention segments / KV-state slots:
     //   [0],[1]: self (own state 0 / 1);  [2]: image 0 reading state 1;  [3]: image 1 reading state 0
-    const Seg segs[4] = {{0, L, L, 0}, {L, S, S, 1}, {0, L, L, 1}, {L, S, S, 0}};
+    const bool fold = attn_fold();
+    const int L1 = fold ? ((L + 2 * kBM - 1) / (2 * kBM)) * (2 * kBM) : L;
+    const int T = L1 + S;
+    ensure_tok(T);
+    tok_.L = L; tok_.L1 = L1; tok_.S = S;
+    const Seg segs[4] = {{0, L, L, 0}, {L1, S, S, 1}, {0, L, L, 1}, {L1, S, S, 0}};
     DFSFM_CUDA(cudaMemcpyAsync(tok_.seg_dev, segs, sizeof(segs), cudaMemcpyHostToDevice, st));
     DFSFM_CUDA(cudaMemcpyAsync(tok_.xf, f0, static_cast<size_t>(L) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    DFSFM_CUDA(cudaMemcpyAsync(tok_.xf + static_cast<long long>(L) * 256, f1, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    split_rows(tok_.xf, L + S, 256, tok_.x[0].hi, tok_.x[0].lo(), st);
+    if (L1 > L) DFSFM_CUDA(cudaMemsetAsync(tok_.xf + static_cast<long long>(L) * 256, 0, static_cast<size_t>(L1 - L) * 256 * sizeof(float), st));
+    DFSFM_CUDA(cudaMemcpyAsync(tok_.xf + static_cast<long long>(L1) * 256, f1, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    split_rows(tok_.xf, T, 256, tok_.x[0].hi, tok_.x[0].lo(), st);
     const int mx = L > S ? L : S;
     for (int li = 0; li < 8; ++li) {
         if ((li % 2) == 0) {  // layer_names = ['self','cross'] * 4 (default.py:22): both images in one pass
-            layer_call(li, true, 0, L + S, 0, L + S, 0, 2, 0, mx, st);
+            layer_call(li, true, 0, T, 0, T, 0, 2, 0, mx, st, fold ? L1 : 0);
         } else {
-            layer_call(li, false, 0, L, L, S, 1, 1, 2, mx, st);  // feat0 attends feat1
-            layer_call(li, false, L, S, 0, L, 0, 1, 3, mx, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
+            layer_call(li, false, 0, L, L1, S, 1, 1, 2, mx, st);  // feat0 attends feat1
+            layer_call(li, false, L1, S, 0, L, 0, 1, 3, mx, st);  // feat1 attends the UPDATED feat0 (transformer.py:96-97)
         }
     }
     DFSFM_CUDA(cudaMemcpyAsync(f0, tok_.xf, static_cast<size_t>(L) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    DFSFM_CUDA(cudaMemcpyAsync(f1, tok_.xf + static_cast<long long>(L) * 256, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    DFSFM_CUDA(cudaMemcpyAsync(f1, tok_.xf + static_cast<long long>(L1) * 256, static_cast<size_t>(S) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
 }
 
 // ------------------------------------------------------------------------------------------------ matching

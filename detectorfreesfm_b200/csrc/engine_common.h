@@ -61,6 +61,7 @@ inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, cons
             // one kernel per epilogue flavour (see LinEpiS)
             if (ep.mode == LIN_F32_ELU) launch_gemm2<BN, kSplit, LinEpiS<LIN_F32_ELU, 0>>(maps, core, ep, n_total, st);
             else if (ep.mode == LIN_RELU_HL) launch_gemm2<BN, kSplit, LinEpiS<LIN_RELU_HL, 0>>(maps, core, ep, n_total, st);
+            else if (ep.mode == LIN_QZ) launch_gemm2<BN, kSplit, LinEpiS<LIN_QZ, 0>>(maps, core, ep, n_total, st);
             else if (ep.resid != nullptr) launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 1>>(maps, core, ep, n_total, st);
             else if (ep.res_hi != nullptr) launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 2>>(maps, core, ep, n_total, st);
             else launch_gemm2<BN, kSplit, LinEpiS<LIN_LN, 0>>(maps, core, ep, n_total, st);
@@ -68,6 +69,7 @@ inline void launch_gemm_counted(const TmapPack& maps, const GemmCore& core, cons
             launch_gemm2<BN, kSplit, Epi>(maps, core, ep, n_total, st);
         }
     } else {
+        if constexpr (std::is_same<Epi, LinEpi>::value) DFSFM_CHECK(ep.mode != LIN_QZ, "LIN_QZ needs engine 2");
         launch_gemm<BN, kSplit, Epi>(maps, core, ep, n_total, st);
     }
 }

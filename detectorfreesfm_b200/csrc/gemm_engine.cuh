@@ -47,6 +47,8 @@ struct GemmCore {
     int cpad;      // K elements per tap in the weight matrix
     int b_row0;    // first weight row (output channel) of this launch
     int bo_mode;   // tap groups only: 1 = put (address >> 7) & 7 into the descriptor's base-offset field for row-shifted starts
+    int seg_mp0;   // engine 2: row-pair tiles (256 rows) >= seg_mp0 read their weight tile seg_b_rows rows further down (0: off) --
+    int seg_b_rows;  //   the two images of a pair carry different per-call "weights" (the attention state folded into merge)
     int8_t tap_map[kMaxTaps];  // which activation map a tap reads
     int tap_shift[kMaxTaps];   // row shift of a tap
     unsigned long long* tl;    // engine 2, debugging: when set, [CTA][16] globaltimer stamps of this launch (dfsfm_debug_timeline)
@@ -229,6 +231,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, 
     return d;
 }
 
+struct EpiNoState {};
+template <class Epi, bool = Epi::kHasState>
+struct EpiStateOf { using type = EpiNoState; };
+template <class Epi>
+struct EpiStateOf<Epi, true> { using type = typename Epi::State; };
+
 template <int BN, bool kSplit, class Epi, int G = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
@@ -282,7 +290,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
                 const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
-                const int nrow = core.b_row0 + nt * BN + static_cast<int>(rank) * (BN / 2);
+                const int nrow = core.b_row0 + nt * BN + static_cast<int>(rank) * (BN / 2) + ((core.seg_mp0 > 0 && mp >= core.seg_mp0) ? core.seg_b_rows : 0);
                 for (int it = 0; it < n_iters; ++it) {
                     const int t = (it / core.kchunks) * G;  // first tap of the group
                     const int c = it % core.kchunks;
@@ -359,24 +367,32 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
         const int cb = half * kHalfCols, ce = half == 0 ? kHalfCols : BN;
         int a = 0;
         uint32_t aphase = 0;
+        EpiCtx ctx;
+        ctx.stg = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + (warp - 2) * Epi::kEpiStageBytes : nullptr;
+        ctx.stg_partner = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + ((warp - 2) ^ 4) * Epi::kEpiStageBytes : nullptr;
+        ctx.bar_id = 1 + quad;
+        // stateful epilogues (KvEpi) carry per-thread accumulators across the tiles of this persistent CTA
+        typename EpiStateOf<Epi>::type est;
+        if constexpr (Epi::kHasState) Epi::init(est);
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
             const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
             const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
             mbar_wait(&tmem_full_bar[a], aphase);
             tc_fence_after();
             if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 6 : 8);  // accumulator of the first / latest tile complete
-            EpiCtx ctx;
-            ctx.stg = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + (warp - 2) * Epi::kEpiStageBytes : nullptr;
-            ctx.stg_partner = Epi::kEpiStageBytes ? smem + Cfg::kEpiOff + ((warp - 2) ^ 4) * Epi::kEpiStageBytes : nullptr;
-            ctx.bar_id = 1 + quad;
-            Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
-                                                 nt * BN, cb, ce, nt * 2 + half, ctx);
+            if constexpr (Epi::kHasState)
+                Epi::template run_state<BN>(ep, est, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, nt,
+                                            half, quad, ctx, smem + Cfg::kEpiOff);
+            else
+                Epi::template run<BN, Cfg::kCorrOff>(ep, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane,
+                                                     nt * BN, cb, ce, nt * 2 + half, ctx);
             tc_fence_before();
             __syncwarp();
             if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 7 : 9);  // epilogue of the first / latest tile done (this warp)
             if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
             if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
         }
+        if constexpr (Epi::kHasState) Epi::finish(ep, est, lane, half, quad, smem + Cfg::kEpiOff);
     }
     tc_fence_before();
     if (threadIdx.x == 0) tl_stamp(core, 10);
@@ -455,6 +471,7 @@ struct ConvEpiParams {
 
 struct ConvEpi {
     using Params = ConvEpiParams;
+    static constexpr bool kHasState = false;
     static constexpr bool kSeparateCorr = true;
     static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>
@@ -583,6 +600,7 @@ enum LinMode : int {
     LIN_F32_ELU = 0,   // fp32 out; elu(x)+1 on output columns < elu_cols (q/k feature map of linear attention)
     LIN_RELU_HL = 1,   // relu -> split-fp16 planes
     LIN_LN = 2,        // LayerNorm over the full row (BN == d_model) [+ residual] -> fp32 and/or split-fp16 planes
+    LIN_QZ = 3,        // q projection of linear attention: Q = elu(q)+1, z = 1/(Q . Ksum_head + eps) per 32-wide head, out = Q*z -> planes
 };
 
 struct LinEpiParams {
@@ -599,6 +617,8 @@ struct LinEpiParams {
     float* out_f32;
     int out_f32_ld;
     int out_col0;        // column offset added to n for the fp32 output
+    const float* ksum;   // LIN_QZ: [segments][N] sum over the source tokens of elu(k)+1 (linear_attention.py:43)
+    int seg_row0;        // LIN_QZ: rows >= seg_row0 belong to segment 1 (ksum + N); 0 = single segment
     __half* out_hi;
     __half* out_lo;
     int out_ld;
@@ -614,6 +634,7 @@ struct LinEpiParams {
 
 struct LinEpi {
     using Params = LinEpiParams;
+    static constexpr bool kHasState = false;
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = 4096;  // engine 2: one 32 x 32 fp32 block per epilogue warp
     template <int BN, int kCorr>
@@ -751,6 +772,24 @@ struct LinEpi {
             const int col = nb + 4 * ch;
             float v[32];
             load_acc32<0>(tmem_warp + c0, v);
+            if (kMode == LIN_QZ) {
+                // this thread holds one head (32 columns) of its row: the normaliser Z of linear_attention.py:43 is row-local.
+                // The message is then msg = (Q*Z) . KV, folded with the merge projection into one GEMM against G = len * KV . Wm^T.
+                const float* ks = p.ksum + ((p.seg_row0 > 0 && row0 + lane >= p.seg_row0) ? p.N : 0) + nb;
+                float dot = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + j));
+                    v[j] = v[j] > 0.f ? v[j] + 1.f : fast_ex2(v[j] * 1.4426950408889634f);
+                    v[j + 1] = v[j + 1] > 0.f ? v[j + 1] + 1.f : fast_ex2(v[j + 1] * 1.4426950408889634f);
+                    v[j + 2] = v[j + 2] > 0.f ? v[j + 2] + 1.f : fast_ex2(v[j + 2] * 1.4426950408889634f);
+                    v[j + 3] = v[j + 3] > 0.f ? v[j + 3] + 1.f : fast_ex2(v[j + 3] * 1.4426950408889634f);
+                    dot = fmaf(v[j], k4.x, dot); dot = fmaf(v[j + 1], k4.y, dot); dot = fmaf(v[j + 2], k4.z, dot); dot = fmaf(v[j + 3], k4.w, dot);
+                }
+                const float z = 1.f / (dot + 1e-6f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] *= z;
+            }
             stage_rows(ctx.stg, lane, v);
             __syncwarp();
             const bool elu = kMode == LIN_F32_ELU && nb < p.elu_cols;
@@ -880,6 +919,7 @@ struct LinEpi {
 template <int kMode, int kRes>
 struct LinEpiS {
     using Params = LinEpiParams;
+    static constexpr bool kHasState = false;
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = LinEpi::kEpiStageBytes;
     template <int BN, int kCorr>
@@ -889,6 +929,129 @@ struct LinEpiS {
         if (DFSFM_DBG(p, 8)) return;
         if (kMode == LIN_LN) LinEpi::run_ln_staged<BN, kRes>(p, tmem_warp, row0, lane, n0, cb, ctx);
         else LinEpi::run_plain_staged<kMode>(p, tmem_warp, row0, lane, n0, cb, ce, ctx);
+    }
+};
+
+// ------------------------------------------------------------------- k/v projection + linear-attention state (engine 2 only)
+// The source tokens' k, v projection with the state reduction of linear_attention.py:40-42 folded into the epilogue:
+//     KV[h][d][v] = sum_s (elu(k[s,h,d]) + 1) * v[s,h,v],      Ksum[h][d] = sum_s (elu(k[s,h,d]) + 1)
+// k and v never reach HBM.  The weight rows are packed so that one 256-column tile holds [K of heads 4t..4t+3 | V of the same heads]
+// (packing.py "kvp"): the warp that owns columns [0,128) of a lane quadrant holds four 32x32 K blocks, its partner warp the matching V
+// blocks.  Per head both blocks go through the per-warp staging buffers and the 64 threads of the pair accumulate the 32x32 outer-
+// product sum over their 32 rows in registers (thread = (d, 16 of the v)); the accumulators live across all tiles of the persistent
+// CTA and are combined over the four lane quadrants through shared memory in a fixed order when the CTA is done with a
+// (segment, column-tile) -- deterministic.  A second tiny kernel (kv_state_final_kernel) adds the per-CTA partials.
+struct KvEpiParams {
+    int M;
+    int seg_row0;      // rows >= seg_row0 (a multiple of 256) belong to segment 1; 0 = one segment
+    int row_begin[2];  // valid rows of a segment: [row_begin, row_end) in launch-relative rows (padding rows contribute nothing)
+    int row_end[2];
+    float* part;       // [2 segments][2 column tiles][gridDim.x CTAs][4 heads * 32 * 33]
+    unsigned* flags;   // [2][2][gridDim.x]: == epoch when the slot was written by this launch
+    unsigned epoch;
+};
+constexpr int kKvPartFloats = 4 * 32 * 33;
+
+struct KvEpi {
+    using Params = KvEpiParams;
+    static constexpr bool kHasState = true;
+    static constexpr bool kSeparateCorr = false;
+    static constexpr int kEpiStageBytes = 4096;
+    struct State {
+        float acc[4][16];
+        float ks[4];
+        int seg, nt;
+    };
+    static __device__ __forceinline__ void reset(State& st) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            st.ks[h] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) st.acc[h][j] = 0.f;
+        }
+    }
+    static __device__ __forceinline__ void init(State& st) {
+        reset(st);
+        st.seg = -1;
+        st.nt = -1;
+    }
+    // combine the four quadrant pairs of this CTA in quadrant order and write the partial of (st.seg, st.nt)
+    static __device__ __forceinline__ void flush(const Params& p, State& st, int lane, int half, int quad, uint8_t* epi_smem) {
+        float* red = reinterpret_cast<float*>(epi_smem);  // 16.5 KB of the 32 KB staging area
+        named_bar_sync(5, 32 * kGemm2EpiWarps);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            if (quad == q) {
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    float* r = red + (h * 32 + lane) * 33 + half * 16;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = (q == 0 ? 0.f : r[j]) + st.acc[h][j];
+                    if (half == 0) red[(h * 32 + lane) * 33 + 32] = (q == 0 ? 0.f : red[(h * 32 + lane) * 33 + 32]) + st.ks[h];
+                }
+            }
+            named_bar_sync(5, 32 * kGemm2EpiWarps);
+        }
+        const long long slot = (static_cast<long long>(st.seg * 2 + st.nt) * gridDim.x + blockIdx.x);
+        float* o = p.part + slot * kKvPartFloats;
+        const int t = (half * 4 + quad) * 32 + lane;
+        for (int i = t; i < kKvPartFloats; i += 32 * kGemm2EpiWarps) o[i] = red[i];
+        if (t == 0) p.flags[slot] = p.epoch;
+        named_bar_sync(5, 32 * kGemm2EpiWarps);
+        reset(st);
+    }
+    template <int BN>
+    static __device__ __forceinline__ void run_state(const Params& p, State& st, uint32_t tmem_warp, int row0, int lane, int nt, int half, int quad,
+                                                     const EpiCtx& ctx, uint8_t* epi_smem) {
+        static_assert(BN == 256, "KvEpi tiles are [4 K heads | 4 V heads]");
+        const int seg = (p.seg_row0 > 0 && row0 >= p.seg_row0) ? 1 : 0;
+        if (st.seg != seg || st.nt != nt) {  // uniform over the CTA's epilogue warps (same tile sequence)
+            if (st.seg >= 0) flush(p, st, lane, half, quad, epi_smem);
+            st.seg = seg;
+            st.nt = nt;
+        }
+        const int row = row0 + lane;
+        const bool valid = row >= p.row_begin[seg] && row < p.row_end[seg];
+        const uint8_t* kst = half == 0 ? ctx.stg : ctx.stg_partner;
+        const uint8_t* vst = half == 0 ? ctx.stg_partner : ctx.stg;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {  // unrolled: the per-head accumulators must stay in registers
+            float v[32];
+            load_acc32<0>(tmem_warp + half * 128 + h * 32, v);
+            if (half == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float e = v[j] > 0.f ? v[j] + 1.f : fast_ex2(v[j] * 1.4426950408889634f);  // elu(x) + 1
+                    v[j] = valid ? e : 0.f;
+                }
+            }
+            LinEpi::stage_rows(ctx.stg, lane, v);
+            named_bar_sync(ctx.bar_id, 64);
+            float ksum = 0.f;
+            float a[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = st.acc[h][j];
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const float k = *reinterpret_cast<const float*>(kst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+                ksum += k;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 w = LinEpi::unstage(vst, r, half * 4 + i);
+                    a[4 * i] = fmaf(k, w.x, a[4 * i]);
+                    a[4 * i + 1] = fmaf(k, w.y, a[4 * i + 1]);
+                    a[4 * i + 2] = fmaf(k, w.z, a[4 * i + 2]);
+                    a[4 * i + 3] = fmaf(k, w.w, a[4 * i + 3]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) st.acc[h][j] = a[j];
+            st.ks[h] += ksum;
+            named_bar_sync(ctx.bar_id, 64);  // both warps are done reading the staged blocks
+        }
+    }
+    static __device__ __forceinline__ void finish(const Params& p, State& st, int lane, int half, int quad, uint8_t* epi_smem) {
+        if (st.seg >= 0) flush(p, st, lane, half, quad, epi_smem);
     }
 };
 
@@ -919,6 +1082,7 @@ __device__ __forceinline__ unsigned long long pack_best(float conf, int idx) {
 
 struct SimEpi {
     using Params = SimEpiParams;
+    static constexpr bool kHasState = false;
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = 0;
     template <int BN, int kCorr>

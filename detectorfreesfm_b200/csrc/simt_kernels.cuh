@@ -281,6 +281,91 @@ static __global__ void __launch_bounds__(256) attn_apply_kernel(const float* __r
     }  // rep
 }
 
+// Sum the per-CTA partial states written by KvEpi (gemm_engine.cuh) in CTA order (deterministic) into the state layout the other
+// kernels use: state[seg.state][(h*32+d)*33 + v], Ksum at v == 32; V's 1/len of linear_attention.py:39 is applied here.
+// grid (ceil(8*32*33 / 64), launch segments), block 256 = 64 outputs x 4 CTA groups.
+static __global__ void __launch_bounds__(256) kv_state_final_kernel(const float* __restrict__ part, const unsigned* __restrict__ flags, unsigned epoch,
+                                                                    int n_ctas, int part_floats, const Seg* __restrict__ segs,
+                                                                    float* __restrict__ state) {
+    constexpr int SZ = 8 * 32 * 33, HS = 32 * 33;
+    __shared__ float red[4][64];
+    const int seg = blockIdx.y;
+    const Seg sg = segs[seg];
+    const int li = threadIdx.x & 63, grp = threadIdx.x >> 6;
+    const int i = blockIdx.x * 64 + li;
+    float s = 0.f;
+    if (i < SZ) {
+        const int h = i / HS, rem = i - h * HS;
+        const int nt = h >> 2, hh = h & 3;
+        const long long slot0 = static_cast<long long>(seg * 2 + nt) * n_ctas;
+        const float* b = part + slot0 * part_floats + hh * HS + rem;
+        const unsigned* f = flags + slot0;
+        for (int c = grp; c < n_ctas; c += 4)
+            if (f[c] == epoch) s += b[static_cast<long long>(c) * part_floats];
+    }
+    red[grp][li] = s;
+    __syncthreads();
+    if (grp == 0 && i < SZ) {
+        const float t = (red[0][li] + red[1][li]) + (red[2][li] + red[3][li]);
+        state[static_cast<long long>(sg.state) * SZ + i] = (i % 33) < 32 ? t / static_cast<float>(sg.count) : t;
+    }
+}
+
+// Fold the attention state into the merge projection (HP-1 coarse layers, where a whole image shares one state):
+//   message = merge( (Q*Z) . KV * len )  ==  (Q*Z) . G^T   with   G[n][h*D+d] = len * sum_v KV[h][d][v] * Wm[n][h*D+v]
+// so that linear attention + merge (transformer.py:47-48, linear_attention.py:42-45) is ONE 256x256 GEMM per token tile against a
+// per-call matrix, and neither q nor the message ever visit HBM as fp32.  grid (8 heads, segments), block 8*D (thread = output
+// channel n).  `segs[i].state` picks the KV state, `.count` is the source length (v_length).  Also emits Ksum as a dense vector.
+template <int D>
+static __global__ void __launch_bounds__(8 * D) attn_fold_merge_kernel(const float* __restrict__ state, const Seg* __restrict__ segs,
+                                                                       const __half* __restrict__ wm_hi, const __half* __restrict__ wm_lo,
+                                                                       __half* __restrict__ g_hi, __half* __restrict__ g_lo,
+                                                                       float* __restrict__ ksum_out) {
+    constexpr int C = 8 * D;
+    constexpr int SZ = C * (D + 1);
+    __shared__ float kv[D][D + 1];
+    const int h = blockIdx.x, seg = blockIdx.y, n = threadIdx.x;
+    const Seg sg = segs[seg];
+    const float* st = state + static_cast<long long>(sg.state) * SZ + (h * D) * (D + 1);
+    for (int i = threadIdx.x; i < D * (D + 1); i += C) kv[i / (D + 1)][i % (D + 1)] = st[i];
+    float w[D];
+#pragma unroll
+    for (int v = 0; v < D; v += 8) {
+        const uint4 uh = *reinterpret_cast<const uint4*>(wm_hi + static_cast<long long>(n) * C + h * D + v);
+        const uint4 ul = *reinterpret_cast<const uint4*>(wm_lo + static_cast<long long>(n) * C + h * D + v);
+        const __half2* hh = reinterpret_cast<const __half2*>(&uh);
+        const __half2* hl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 a = __half22float2(hh[q]), b = __half22float2(hl[q]);
+            w[v + 2 * q] = a.x + b.x;
+            w[v + 2 * q + 1] = a.y + b.y;
+        }
+    }
+    __syncthreads();
+    const float len = static_cast<float>(sg.count);
+    if (n < D) ksum_out[seg * C + h * D + n] = kv[n][D];
+    const long long o = (static_cast<long long>(seg) * C + n) * C + h * D;
+#pragma unroll
+    for (int d0 = 0; d0 < D; d0 += 8) {
+        uint4 uh, ul;
+        uint32_t* ph = reinterpret_cast<uint32_t*>(&uh);
+        uint32_t* pl = reinterpret_cast<uint32_t*>(&ul);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int v = 0; v < D; ++v) {
+                a0 = fmaf(kv[d0 + 2 * q][v], w[v], a0);
+                a1 = fmaf(kv[d0 + 2 * q + 1][v], w[v], a1);
+            }
+            split_f16x2(a0 * len, a1 * len, ph[q], pl[q]);
+        }
+        *reinterpret_cast<uint4*>(g_hi + o + d0) = uh;
+        *reinterpret_cast<uint4*>(g_lo + o + d0) = ul;
+    }
+}
+
 // --------------------------------------------------------------------------------------------------------
 // merge per-column-tile softmax partials (log2 domain) into lse[i] = max + log2(sum 2^(. - max))
 static __global__ void stats_merge_kernel(const float2* __restrict__ part, int T, int M, float* __restrict__ lse) {

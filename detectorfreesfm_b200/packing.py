@@ -104,6 +104,10 @@ def pack_loftr(sd, fine=False):
     for i in range(8):
         p = f"loftr_coarse.layers.{i}"
         put(f"tr.{i}.qkv", torch.cat([sd[p + ".q_proj.weight"], sd[p + ".k_proj.weight"], sd[p + ".v_proj.weight"]], 0), 0)
+        # k/v projection with the state reduction in the GEMM epilogue (KvEpi): each 256-row weight tile = [K rows of heads 4t..4t+3 |
+        # V rows of the same heads], so that one output tile holds both factors of its heads' K^T V products
+        wk, wv = sd[p + ".k_proj.weight"], sd[p + ".v_proj.weight"]
+        put(f"tr.{i}.kvp", torch.cat([wk[:128], wv[:128], wk[128:], wv[128:]], 0), 0)
         put(f"tr.{i}.merge", sd[p + ".merge.weight"], 0)
         put(f"tr.{i}.mlp0", sd[p + ".mlp.0.weight"], 0)
         put(f"tr.{i}.mlp2", sd[p + ".mlp.2.weight"], 0)
