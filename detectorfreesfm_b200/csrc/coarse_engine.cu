@@ -145,6 +145,15 @@ static bool kv_epi() {
     }
     return v == 1;
 }
+// DFSFM_ENC_FUSED=0: q / merge / mlp.0 / mlp.2 as four GEMM launches (A/B reference for the fused encoder-layer kernel)
+static bool enc_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_ENC_FUSED");
+        v = (e && e[0] == '1') ? 1 : 0;   // opt-in until validated on hardware
+    }
+    return v == 1;
+}
 static bool lin_bn128() {  // A/B switch: 128-wide N tiles for the wide linears (QKV, KV, mlp.0): twice the tiles, better last-round fill
     static int v = -1;
     if (v < 0) {
@@ -499,6 +508,22 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
           attn_fold_merge_kernel<32><<<dim3(8, n_segs), 256, 0, st>>>(tok_.kv_state, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(), tok_.g.hi, tok_.g.lo(),
                                                                   tok_.ksum); }
         DFSFM_CUDA(cudaGetLastError());
+        if (enc_fused() && res_hl()) {
+            // (4-7) everything on the attending rows in ONE kernel: q + normaliser, attention/merge, norm1, mlp, norm2 + residual
+            EncParams ep;
+            memset(&ep, 0, sizeof(ep));
+            ep.seg_tile0 = seg_row0 / (2 * kBM);
+            ep.ksum = tok_.ksum;
+            ep.ln1_g = params.vec(p + ".ln1.g"); ep.ln1_b = params.vec(p + ".ln1.b");
+            LinEpiParams& e4 = ep.e4;
+            e4.M = xn; e4.N = 256; e4.mode = LIN_LN;
+            e4.gamma = params.vec(p + ".ln2.g"); e4.beta = params.vec(p + ".ln2.b");
+            e4.res_hi = tok_.x[0].hi + static_cast<long long>(x0) * 256; e4.res_lo = tok_.x[0].lo() + static_cast<long long>(x0) * 256; e4.res_ld = 256;
+            e4.out_hi = tok_.x[0].hi + static_cast<long long>(x0) * 256; e4.out_lo = tok_.x[0].lo() + static_cast<long long>(x0) * 256; e4.out_ld = 256;
+            if (li == 7) { e4.out_f32 = xf + static_cast<long long>(x0) * 256; e4.out_f32_ld = 256; }
+            launch_enc256_fused(tok_.x[0], x0, xn, params.mat(p + ".qkv"), tok_.g, params.mat(p + ".mlp0"), params.mat(p + ".mlp2"), ep, st);
+            return;
+        }
         // (4) q of the attending rows with the normaliser folded in: Q*Z -> split planes (the msg buffer)
         {
             TmapPack maps;

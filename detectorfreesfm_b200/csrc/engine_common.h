@@ -7,6 +7,7 @@
 #include <string>
 
 #include "host_utils.h"
+#include "encoder_fused.cuh"
 #include "mlp_fused.cuh"
 #include "simt_kernels.cuh"
 
@@ -114,6 +115,37 @@ inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     DFSFM_CUDA(cudaLaunchKernelEx(&cfg, mlp128_fused_kernel, maps, p, tiles));
+}
+
+// Fused encoder layer (encoder_fused.cuh): q projection + normaliser, attention/merge GEMM, LayerNorm1, mlp, LayerNorm2 + residual
+// for the token rows [row0, row0 + T) of `x`.  `wqkv` rows [0,256) are Wq; `g` holds the folded matrix of each segment.
+inline void launch_enc256_fused(const HL& x, long long row0, long long T, const HL& wqkv, const HL& g, const HL& w0, const HL& w2, EncParams p,
+                                cudaStream_t st) {
+    static PerDeviceOnce once;
+    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(enc256_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
+    EncMaps maps;
+    maps.x = make_tmap(x.hi + row0 * 256, 256, T, x.plane_elems(), 128);
+    maps.wq = make_tmap(wqkv.hi, 256, 256, wqkv.plane_elems(), 128);
+    maps.g = make_tmap(g, 128);
+    maps.w0 = make_tmap(w0, 128);
+    maps.w2 = make_tmap(w2, 128);
+    p.T = static_cast<int>(T);
+    const int tiles = static_cast<int>((T + 2 * kBM - 1) / (2 * kBM));
+    const int max_clusters = sm_count() / 2;
+    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    LaunchScope ls("enc_fused", st);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(kEncThreads);
+    cfg.dynamicSmemBytes = kEncSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, enc256_fused_kernel, maps, p, tiles));
 }
 
 // 3x3 stride-1 convolutions with BN <= 128: the three dx taps of a kernel row share one activation slab (engine 2 only).
