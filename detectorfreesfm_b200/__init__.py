@@ -5,7 +5,7 @@ Host side = thin Python mirroring the reference's plugin interfaces; device side
 """
 from ._lib import DfsfmError, load_library  # noqa: F401
 
-__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher", "KeypointMerger", "merge_keypoints", "GpuImageReader", "B200CoarseMatchingDataset"]
+__all__ = ["DfsfmError", "load_library", "B200LoFTR", "B200MultiviewMatcher", "KeypointMerger", "merge_keypoints", "GpuImageReader", "B200CoarseMatchingDataset", "B200MatchingMultiviewData"]
 
 
 def __getattr__(name):
@@ -21,4 +21,7 @@ def __getattr__(name):
     if name in ("GpuImageReader", "B200CoarseMatchingDataset"):
         from . import image_pipeline
         return getattr(image_pipeline, name)
+    if name == "B200MatchingMultiviewData":
+        from .chunk_dataset import B200MatchingMultiviewData
+        return B200MatchingMultiviewData
     raise AttributeError(name)

@@ -46,6 +46,12 @@ PROTOTYPES = {
     "dfsfm_refine_set_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_int64, c_int]),
     "dfsfm_refine_chunk": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dfsfm_assign_bags": (c_int, [ctypes.POINTER(c_void_p), c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_int]),
+    "dfsfm_bags_sizes": (None, [c_void_p, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
+    "dfsfm_bags_export": (None, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dfsfm_bags_destroy": (None, [c_void_p]),
+    "dfsfm_debug_pyset": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, ctypes.POINTER(c_int64)]),
     "dfsfm_debug_gemm": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                  c_int, c_int, c_void_p]),
 }

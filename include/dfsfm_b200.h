@@ -121,6 +121,27 @@ int dfsfm_resize_lanczos_gray(const uint8_t* img_dev, int h, int w, int64_t ld, 
                               const int32_t* ybounds_dev, const int32_t* ycoef_dev, int yksize, int out_h, int out_w, uint8_t* tmp_dev,
                               float* out_dev, void* stream);
 
+/* --------------------------------------------------------------------- bag assignment + chunking (host) */
+/* FeatureTrackStatus / assign_bags / chunk_bags of src/post_optimization/data_construct/construct_matching_data.py:10-261 and
+ * chunks_balance (src/utils/ray_utils.py:100-108) on flat arrays; all pointers are HOST pointers.
+ *   tracks   n_tracks feature tracks in the order of point_cloud_assigned_imgID_kptID: track_ids (point3D ids), ref_img_ids (assigned
+ *            reference image), obs_offset [n_tracks+1] / obs_img_ids: the raw point3D.image_ids of every track (duplicates included);
+ *   frames   keyframe_dict as CSR: frame_img_ids [n_frames], frame_offset [n_frames+1], frame_track_ids (point3D ids whose reference
+ *            node lies on the image, key-point order);
+ *   max_track_length, max_num_img_in_bag (<= 0: = max_track_length), chunk (tracks per chunk; <= 0: no chunking).
+ * The result handle holds the CHUNKED bags in the reference's order (incl. CPython's set iteration order of the image ids). */
+typedef struct dfsfm_bags dfsfm_bags_t;
+int dfsfm_assign_bags(dfsfm_bags_t** out, int64_t n_tracks, const int64_t* track_ids, const int64_t* ref_img_ids, const int64_t* obs_offset,
+                      const int64_t* obs_img_ids, int64_t n_frames, const int64_t* frame_img_ids, const int64_t* frame_offset,
+                      const int64_t* frame_track_ids, int max_track_length, int max_num_img_in_bag, int chunk);
+void dfsfm_bags_sizes(const dfsfm_bags_t* h, int64_t* n_bags, int64_t* n_bag_images, int64_t* n_tracks, int64_t* n_query);
+/* bag_img_off [n_bags+1] / bag_img; bag_trk_off [n_bags+1] / trk_id, trk_ref [n_tracks]; trk_q_off [n_tracks+1] / trk_q */
+void dfsfm_bags_export(const dfsfm_bags_t* h, int64_t* bag_img_off, int64_t* bag_img, int64_t* bag_trk_off, int64_t* trk_id, int64_t* trk_ref,
+                       int64_t* trk_q_off, int64_t* trk_q);
+void dfsfm_bags_destroy(dfsfm_bags_t* h);
+/* test hook: one CPython-set expression on small integers, result in iteration order (see csrc/bag_assign.cpp) */
+int dfsfm_debug_pyset(int op, const int64_t* a, int64_t na, const int64_t* b, int64_t nb, int64_t* out, int64_t* n_out);
+
 /* -------------------------------------------------------------------------------------------------- test / bench hooks */
 /* Shifted-row GEMM engine on raw split-fp16 operands: out[M][N] fp32 = sum_t A[p+shift_t, :cpad] . W[n, t*cpad : (t+1)*cpad].
  * a_dev: [2][a_rows][C] halves, w_dev: [2][w_rows][taps*cpad] halves.  bn in {64,128,208,256}; split in {0,1}. */

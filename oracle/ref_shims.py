@@ -407,3 +407,26 @@ def import_hook_modules():
     mm = importlib.import_module("src.post_optimization.matcher_model.multiview_match")
     mmw = importlib.import_module("src.post_optimization.matcher_model.multiview_match_worker")
     return cm, cmw, mm, mmw
+
+
+def import_chunk_dataset():
+    """-> the reference's ``MatchingMultiviewData`` class (src/post_optimization/data_construct/construct_matching_data.py; SURVEY 8(a) row
+    b2 / 8(f) row 2), imported where it lies: its own geometry helpers and ``chunks_balance`` are the real files, ray / loguru are inert."""
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    utils = _mod("src.utils")
+    utils.__path__ = [os.path.join(REF, "src", "utils")]
+    colmap = _mod("src.utils.colmap")
+    colmap.__path__ = [os.path.join(REF, "src", "utils", "colmap")]
+    _stub_ray()
+    po_ = _mod("src.post_optimization")
+    po_.__path__ = [os.path.join(REF, "src", "post_optimization")]
+    pu = _mod("src.post_optimization.utils")
+    pu.__path__ = [os.path.join(REF, "src", "post_optimization", "utils")]
+    dc = _mod("src.post_optimization.data_construct")
+    dc.__path__ = [os.path.join(REF, "src", "post_optimization", "data_construct")]
+    mod = importlib.import_module("src.post_optimization.data_construct.construct_matching_data")
+    return mod.MatchingMultiviewData

@@ -145,5 +145,20 @@ def postprocess_golden():
     return {"names": names, "matches": matches, "final_keypoints": fk, "final_scores": fs, "updated_matches": upd}
 
 
+def chunk_dataset_golden():
+    """the reference's own MatchingMultiviewData (bags + every chunk dict) on one synthetic COLMAP model"""
+    Ref = ref_shims.import_chunk_dataset()
+    case = dict(n_images=24, n_points=500, max_obs=20, seed=5, dup_frac=0.1)
+    cfg = {"max_track_length": 16, "chunk": 60}
+    ref = Ref(util.SynthColmapDataset(**case), cfg)
+    bags = [{"bag_image_ids": [int(x) for x in b["bag_image_ids"]], "track_ids": [int(x) for x in b["track_ids"]],
+             "track_corresponding_imgs": [[int(r), [int(x) for x in q]] for r, q in b["track_corresponding_imgs"]]} for b in ref.image_bags]
+    return {"case": case, "cfg": cfg, "bags": bags, "items": [{k: v for k, v in ref[i].items() if k != "images"} for i in range(len(ref))]}   # images: pass-through of ds[...]
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "chunk_dataset":
+        torch.save(chunk_dataset_golden(), os.path.join(HERE, "chunk_dataset_small.pt"))
+    else:
+        main()
+        torch.save(chunk_dataset_golden(), os.path.join(HERE, "chunk_dataset_small.pt"))

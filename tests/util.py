@@ -189,3 +189,68 @@ def to_cuda(data):
         else:
             out[k] = v
     return out
+
+
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class SynthColmapDataset:
+    """The attributes and item protocol of ``CoarseColmapDataset`` (src/dataset/coarse_sfm_refinement_dataset.py) that the chunk
+    dataset reads -- colmap_images / colmap_3ds / image_intrin_extrins / keyframe_dict / point_cloud_assigned_imgID_kptID /
+    colmapID2frameID_dict and ``ds[frame] -> {'image', 'scale'}`` -- over a seeded synthetic reconstruction: cameras on a ring looking
+    at a point cloud, every 3-D point observed by 2..max_obs images (sometimes twice by the same image, as COLMAP tracks do), the
+    reference node of a track chosen by the 'middle scale' rule of get_keyframes_by_scale (:236-297)."""
+
+    def __init__(self, n_images=12, n_points=400, max_obs=9, seed=0, hw=(48, 64), dup_frac=0.05, first_image_id=1):
+        rng = np.random.default_rng(seed)
+        self.img_list = [f"img_{i:04d}.jpg" for i in range(n_images)]
+        img_ids = [first_image_id + 3 * i for i in range(n_images)]            # non-contiguous ids, like a filtered COLMAP model
+        self.colmapID2frameID_dict = {cid: f for f, cid in enumerate(img_ids)}
+        self.image_intrin_extrins = {}
+        for k, cid in enumerate(img_ids):
+            a = 2 * np.pi * k / n_images
+            c = np.array([4 * np.cos(a), 4 * np.sin(a), 0.3 * np.sin(3 * a)])
+            z = -c / np.linalg.norm(c)
+            x = np.cross([0, 0, 1.0], z); x /= np.linalg.norm(x)
+            y = np.cross(z, x)
+            R = np.stack([x, y, z])
+            f = 500.0 + 20 * k
+            self.image_intrin_extrins[cid] = {"intrin": np.array([[f, 0, hw[1] / 2], [0, f, hw[0] / 2], [0, 0, 1.0]]), "extrin": [R, -R @ c]}
+        xyz = rng.normal(0, 0.6, (n_points, 3))
+        n_kpts = {cid: 0 for cid in img_ids}
+        xys = {cid: [] for cid in img_ids}
+        self.colmap_3ds, self.point_cloud_assigned_imgID_kptID = {}, {}
+        state = {cid: [] for cid in img_ids}
+        for p in range(n_points):
+            pid = 10 + 7 * p
+            k = int(rng.integers(2, max_obs + 1))
+            obs = rng.choice(img_ids, size=min(k, n_images), replace=False).tolist()
+            if rng.random() < dup_frac:
+                obs.append(obs[int(rng.integers(0, len(obs)))])              # the same image twice in one track
+            p2d = []
+            for cid in obs:
+                K, (R, t) = self.image_intrin_extrins[cid]["intrin"], self.image_intrin_extrins[cid]["extrin"]
+                pc = K @ (R @ xyz[p] + t)
+                xys[cid].append(pc[:2] / pc[2] + rng.normal(0, 0.5, 2))
+                state[cid].append(-3)
+                p2d.append(n_kpts[cid])
+                n_kpts[cid] += 1
+            scales = [self.image_intrin_extrins[c]["intrin"][0, 0] / ((self.image_intrin_extrins[c]["intrin"] @ (self.image_intrin_extrins[c]["extrin"][0] @ xyz[p] + self.image_intrin_extrins[c]["extrin"][1]))[2] + 1e-4) for c in obs]
+            a_idx = int(np.argsort(np.array(scales))[len(obs) // 2])
+            self.colmap_3ds[pid] = _NS(xyz=xyz[p], image_ids=np.array(obs, dtype=np.int64), point2D_idxs=np.array(p2d, dtype=np.int64))
+            self.point_cloud_assigned_imgID_kptID[pid] = (np.int64(obs[a_idx]), np.int64(p2d[a_idx]))
+            state[obs[a_idx]][p2d[a_idx]] = pid
+        self.colmap_images = {cid: _NS(xys=np.array(xys[cid], dtype=np.float64).reshape(-1, 2)) for cid in img_ids}
+        self.keyframe_dict = {cid: np.array([s for s in state[cid] if s >= 0], dtype=np.int32) for cid in img_ids}
+        self.colmap_cameras = {}
+        g = torch.Generator().manual_seed(seed)
+        self._items = [{"image": torch.rand(3, hw[0] + 8 * (i % 2), hw[1], generator=g), "scale": torch.tensor([1.0 + 0.25 * (i % 3), 1.5 - 0.25 * (i % 2)]),
+                        "f_name": n, "img_name": n, "frameID": i, "img_path": [n]} for i, n in enumerate(self.img_list)]
+
+    def __len__(self):
+        return len(self.img_list)
+
+    def __getitem__(self, idx):
+        return self._items[idx]
