@@ -148,8 +148,8 @@ def postprocess_golden():
 def chunk_dataset_golden():
     """the reference's own MatchingMultiviewData (bags + every chunk dict) on one synthetic COLMAP model"""
     Ref = ref_shims.import_chunk_dataset()
-    case = dict(n_images=24, n_points=500, max_obs=20, seed=5, dup_frac=0.1)
-    cfg = {"max_track_length": 16, "chunk": 60}
+    case = dict(n_images=20, n_points=160, max_obs=18, seed=5, dup_frac=0.1)
+    cfg = {"max_track_length": 16, "chunk": 40}
     ref = Ref(util.SynthColmapDataset(**case), cfg)
     bags = [{"bag_image_ids": [int(x) for x in b["bag_image_ids"]], "track_ids": [int(x) for x in b["track_ids"]],
              "track_corresponding_imgs": [[int(r), [int(x) for x in q]] for r, q in b["track_corresponding_imgs"]]} for b in ref.image_bags]
