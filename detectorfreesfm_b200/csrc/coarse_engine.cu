@@ -455,6 +455,8 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
     float* xf = tok_.xf;
     auto rows_map = [&](const HL& b, int r0, int n) { return make_tmap(b.hi + static_cast<long long>(r0) * b.C, b.C, n, b.plane_elems(), kBM); };
     const bool fold = attn_fold();
+    // v_length of each source segment of this call (self: image 0 / image 1 themselves; cross: the one source image)
+    const float qz_len[2] = {static_cast<float>(seg_row0 > 0 ? tok_.L : sn), static_cast<float>(tok_.S)};
     if (fold && kv_epi()) {
         // (1+2) k, v projection of the source rows with the linear-attention state reduced in the GEMM epilogue (KvEpi)
         TmapPack maps;
@@ -475,9 +477,11 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
         const int n_ctas = 2 * std::min(tiles, sm_count() / 2);
         { LaunchScope ls("kvproj", st);
           launch_gemm2<256, true, KvEpi>(maps, c, ke, 512, st); }
-        { LaunchScope ls("kv_final", st);
-          kv_state_final_kernel<<<dim3((8 * 32 * 33 + 63) / 64, n_segs), 256, 0, st>>>(tok_.kvp_part, tok_.kvp_flags, ke.epoch, n_ctas, kKvPartFloats,
-                                                                                    tok_.seg_dev + kv_seg0, tok_.kv_state); }
+        // (3) partial states -> V/len -> G = KV . Wm^T and Ksum, in one kernel
+        { const HL& wm = params.mat(p + ".merge");
+          LaunchScope ls("fold", st);
+          kvp_fold_kernel<<<dim3(8, n_segs), 1024, 0, st>>>(tok_.kvp_part, tok_.kvp_flags, ke.epoch, n_ctas, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(),
+                                                         tok_.g.hi, tok_.g.lo(), tok_.ksum); }
         DFSFM_CUDA(cudaGetLastError());
     }
     if (fold && !kv_epi()) {
@@ -502,8 +506,9 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
                                                                                    tok_.kv_state, kv_tok()); }
     }
     if (fold) {
-        // (3) fold the state into the merge projection: G = len * KV . Wm^T per segment, Ksum as a dense vector
-        { const HL& wm = params.mat(p + ".merge");
+        // (3) fold the state into the merge projection: G = KV . Wm^T per segment, Ksum as a dense vector
+        if (!kv_epi()) {
+          const HL& wm = params.mat(p + ".merge");
           LaunchScope ls("fold", st);
           attn_fold_merge_kernel<32><<<dim3(8, n_segs), 256, 0, st>>>(tok_.kv_state, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(), tok_.g.hi, tok_.g.lo(),
                                                                   tok_.ksum); }
@@ -514,6 +519,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             memset(&ep, 0, sizeof(ep));
             ep.seg_tile0 = seg_row0 / (2 * kBM);
             ep.ksum = tok_.ksum;
+            ep.qz_scale[0] = qz_len[0]; ep.qz_scale[1] = qz_len[1];
             ep.ln1_g = params.vec(p + ".ln1.g"); ep.ln1_b = params.vec(p + ".ln1.b");
             LinEpiParams& e4 = ep.e4;
             e4.M = xn; e4.N = 256; e4.mode = LIN_LN;
@@ -531,6 +537,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
             for (int i = 0; i < kMaxAMaps; ++i) maps.a[i] = rows_map(tok_.x[0], x0, xn);
             memset(&e, 0, sizeof(e));
             e.mode = LIN_QZ; e.ksum = tok_.ksum; e.seg_row0 = seg_row0;
+            e.qz_scale[0] = qz_len[0]; e.qz_scale[1] = qz_len[1];
             c.M = xn; c.b_row0 = 0;
             e.M = xn; e.N = 256;
             e.out_hi = tok_.msg[0].hi + static_cast<long long>(x0) * 256; e.out_lo = tok_.msg[0].lo() + static_cast<long long>(x0) * 256; e.out_ld = 256;

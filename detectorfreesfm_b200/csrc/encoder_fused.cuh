@@ -2,7 +2,7 @@
 // transformer.py:35-58 after the k/v state of the source has been reduced -- KvEpi + attn_fold_merge_kernel):
 //
 //     q   = x . Wq^T ;  Q = elu(q)+1 ;  Z = 1/(Q . Ksum_head + eps)                         (linear_attention.py:32,43)
-//     mg  = (Q*Z) . G^T                      G = len * KV . Wm^T : attention + merge in one GEMM     (:44-45, transformer.py:48)
+//     mg  = (Q*Z*len) . G^T                  G = KV . Wm^T : attention + merge in one GEMM           (:44-45, transformer.py:48)
 //     m   = LayerNorm1(mg)
 //     hid = relu([x | m] . W0^T)             512 wide                                           (transformer.py:52)
 //     out = x + LayerNorm2(hid . W2^T)                                                          (:53-55)
@@ -46,6 +46,7 @@ struct EncParams {
     int T;                 // token rows of this launch
     int seg_tile0;         // tiles >= seg_tile0 belong to segment 1 (its G rows and Ksum); <= 0: one segment
     const float* ksum;     // [2][256]
+    float qz_scale[2];     // per segment: source length (Q*Z*len is O(1); see LinEpiParams::qz_scale)
     const float* ln1_g;
     const float* ln1_b;
     LinEpiParams e4;       // LayerNorm2 + residual + stores (M, N = 256, gamma/beta, res_hi/lo, out_hi/lo[, out_f32])
@@ -285,7 +286,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     v[j + 3] = v[j + 3] > 0.f ? v[j + 3] + 1.f : fast_ex2(v[j + 3] * 1.4426950408889634f);
                     dot = fmaf(v[j], k4.x, dot); dot = fmaf(v[j + 1], k4.y, dot); dot = fmaf(v[j + 2], k4.z, dot); dot = fmaf(v[j + 3], k4.w, dot);
                 }
-                const float z = 1.f / (dot + 1e-6f);
+                const float z = p.qz_scale[seg] / (dot + 1e-6f);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= z;
                 uint32_t pk[32];

@@ -619,6 +619,8 @@ struct LinEpiParams {
     int out_col0;        // column offset added to n for the fp32 output
     const float* ksum;   // LIN_QZ: [segments][N] sum over the source tokens of elu(k)+1 (linear_attention.py:43)
     int seg_row0;        // LIN_QZ: rows >= seg_row0 belong to segment 1 (ksum + N); 0 = single segment
+    float qz_scale[2];   // LIN_QZ: per segment, the source length v_length (linear_attention.py:39,45): Q*Z*len is O(1) -- without it the
+                         //   values (~1/len) would sink into the fp16 subnormals of the split planes
     __half* out_hi;
     __half* out_lo;
     int out_ld;
@@ -775,7 +777,8 @@ struct LinEpi {
             if (kMode == LIN_QZ) {
                 // this thread holds one head (32 columns) of its row: the normaliser Z of linear_attention.py:43 is row-local.
                 // The message is then msg = (Q*Z) . KV, folded with the merge projection into one GEMM against G = len * KV . Wm^T.
-                const float* ks = p.ksum + ((p.seg_row0 > 0 && row0 + lane >= p.seg_row0) ? p.N : 0) + nb;
+                const int sg = (p.seg_row0 > 0 && row0 + lane >= p.seg_row0) ? 1 : 0;
+                const float* ks = p.ksum + sg * p.N + nb;
                 float dot = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
@@ -786,7 +789,7 @@ struct LinEpi {
                     v[j + 3] = v[j + 3] > 0.f ? v[j + 3] + 1.f : fast_ex2(v[j + 3] * 1.4426950408889634f);
                     dot = fmaf(v[j], k4.x, dot); dot = fmaf(v[j + 1], k4.y, dot); dot = fmaf(v[j + 2], k4.z, dot); dot = fmaf(v[j + 3], k4.w, dot);
                 }
-                const float z = 1.f / (dot + 1e-6f);
+                const float z = p.qz_scale[sg] / (dot + 1e-6f);
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] *= z;
             }

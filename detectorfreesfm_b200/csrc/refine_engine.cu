@@ -382,10 +382,16 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
           fine_match_kernel<<<M, kFmThreads, smem, st>>>(xf_.p, d_tracks_.p, d_views_.p, Nq, W_, LW_, d_query_.p, d_ref_.p, d_std_.p, M); }
         DFSFM_CUDA(cudaGetLastError());
     }
-    DFSFM_CUDA(cudaMemcpyAsync(query_refined, d_query_.p, static_cast<size_t>(M) * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    DFSFM_CUDA(cudaMemcpyAsync(ref_refined, d_ref_.p, static_cast<size_t>(Nq) * M * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    DFSFM_CUDA(cudaMemcpyAsync(std_out, d_std_.p, static_cast<size_t>(Nq) * M * sizeof(float), cudaMemcpyDeviceToHost, st));
-    DFSFM_CUDA(cudaStreamSynchronize(st));
+    // results: device pointers (the plugin path: they stay on the GPU, nothing synchronises here) or host pointers (copied back, stream
+    // synchronised before returning)
+    cudaPointerAttributes attr;
+    bool dev_out = false;
+    if (cudaPointerGetAttributes(&attr, query_refined) == cudaSuccess) dev_out = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+    else cudaGetLastError();
+    DFSFM_CUDA(cudaMemcpyAsync(query_refined, d_query_.p, static_cast<size_t>(M) * 2 * sizeof(float), cudaMemcpyDefault, st));
+    DFSFM_CUDA(cudaMemcpyAsync(ref_refined, d_ref_.p, static_cast<size_t>(Nq) * M * 2 * sizeof(float), cudaMemcpyDefault, st));
+    DFSFM_CUDA(cudaMemcpyAsync(std_out, d_std_.p, static_cast<size_t>(Nq) * M * sizeof(float), cudaMemcpyDefault, st));
+    if (!dev_out) DFSFM_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace dfsfm

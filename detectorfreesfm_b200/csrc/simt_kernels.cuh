@@ -312,7 +312,7 @@ static __global__ void __launch_bounds__(256) kv_state_final_kernel(const float*
 }
 
 // Fold the attention state into the merge projection (HP-1 coarse layers, where a whole image shares one state):
-//   message = merge( (Q*Z) . KV * len )  ==  (Q*Z) . G^T   with   G[n][h*D+d] = len * sum_v KV[h][d][v] * Wm[n][h*D+v]
+//   message = merge( (Q*Z) . KV * len )  ==  (Q*Z*len) . G^T   with   G[n][h*D+d] = sum_v KV[h][d][v] * Wm[n][h*D+v]
 // so that linear attention + merge (transformer.py:47-48, linear_attention.py:42-45) is ONE 256x256 GEMM per token tile against a
 // per-call matrix, and neither q nor the message ever visit HBM as fp32.  grid (8 heads, segments), block 8*D (thread = output
 // channel n).  `segs[i].state` picks the KV state, `.count` is the source length (v_length).  Also emits Ksum as a dense vector.
@@ -343,7 +343,6 @@ static __global__ void __launch_bounds__(8 * D) attn_fold_merge_kernel(const flo
         }
     }
     __syncthreads();
-    const float len = static_cast<float>(sg.count);
     if (n < D) ksum_out[seg * C + h * D + n] = kv[n][D];
     const long long o = (static_cast<long long>(seg) * C + n) * C + h * D;
 #pragma unroll
@@ -359,11 +358,78 @@ static __global__ void __launch_bounds__(8 * D) attn_fold_merge_kernel(const flo
                 a0 = fmaf(kv[d0 + 2 * q][v], w[v], a0);
                 a1 = fmaf(kv[d0 + 2 * q + 1][v], w[v], a1);
             }
-            split_f16x2(a0 * len, a1 * len, ph[q], pl[q]);
+            split_f16x2(a0, a1, ph[q], pl[q]);
         }
         *reinterpret_cast<uint4*>(g_hi + o + d0) = uh;
         *reinterpret_cast<uint4*>(g_lo + o + d0) = ul;
     }
+}
+
+// The same fold fed directly by the per-CTA partial states of KvEpi: one kernel sums the partials of its head in CTA order
+// (deterministic), applies V's 1/len, and writes G and Ksum -- the state itself never goes back to HBM.
+// grid (8 heads, launch segments), block 1024 = 4 CTA groups x 256 (sum) / 4 d-groups x 256 output channels (fold).
+static __global__ void __launch_bounds__(1024) kvp_fold_kernel(const float* __restrict__ part, const unsigned* __restrict__ flags, unsigned epoch,
+                                                               int n_ctas, const Seg* __restrict__ segs, const __half* __restrict__ wm_hi,
+                                                               const __half* __restrict__ wm_lo, __half* __restrict__ g_hi, __half* __restrict__ g_lo,
+                                                               float* __restrict__ ksum_out) {
+    constexpr int D = 32, C = 256, HS = D * (D + 1), PF = 4 * HS;
+    __shared__ float red[4][HS];
+    __shared__ float kv[D][D + 1];
+    __shared__ unsigned char ok[160];
+    const int h = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x;
+    const Seg sg = segs[seg];
+    const int nt = h >> 2, hh = h & 3;
+    const long long slot0 = static_cast<long long>(seg * 2 + nt) * n_ctas;
+    for (int c = tid; c < n_ctas; c += 1024) ok[c] = flags[slot0 + c] == epoch;
+    __syncthreads();
+    const int grp = tid >> 8, t = tid & 255;
+    const float* base = part + slot0 * PF + hh * HS;
+    for (int e = t; e < HS; e += 256) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int c = grp; c < n_ctas; c += 4)
+            if (ok[c]) s += base[static_cast<long long>(c) * PF + e];
+        red[grp][e] = s;
+    }
+    __syncthreads();
+    const float inv_len = 1.f / static_cast<float>(sg.count);
+    for (int e = tid; e < HS; e += 1024) {
+        const float v = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
+        (&kv[0][0])[e] = (e % (D + 1)) < D ? v * inv_len : v;
+    }
+    __syncthreads();
+    if (tid < D) ksum_out[seg * C + h * D + tid] = kv[tid][D];
+    const int n = t, d0 = grp * 8;
+    float w[D];
+#pragma unroll
+    for (int v = 0; v < D; v += 8) {
+        const uint4 uh = *reinterpret_cast<const uint4*>(wm_hi + static_cast<long long>(n) * C + h * D + v);
+        const uint4 ul = *reinterpret_cast<const uint4*>(wm_lo + static_cast<long long>(n) * C + h * D + v);
+        const __half2* ph = reinterpret_cast<const __half2*>(&uh);
+        const __half2* pl = reinterpret_cast<const __half2*>(&ul);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 a = __half22float2(ph[q]), b = __half22float2(pl[q]);
+            w[v + 2 * q] = a.x + b.x;
+            w[v + 2 * q + 1] = a.y + b.y;
+        }
+    }
+    uint4 uh, ul;
+    uint32_t* oh = reinterpret_cast<uint32_t*>(&uh);
+    uint32_t* ol = reinterpret_cast<uint32_t*>(&ul);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < D; ++v) {
+            a0 = fmaf(kv[d0 + 2 * q][v], w[v], a0);
+            a1 = fmaf(kv[d0 + 2 * q + 1][v], w[v], a1);
+        }
+        split_f16x2(a0, a1, oh[q], ol[q]);
+    }
+    const long long o = (static_cast<long long>(seg) * C + n) * C + h * D + d0;
+    *reinterpret_cast<uint4*>(g_hi + o) = uh;
+    *reinterpret_cast<uint4*>(g_lo + o) = ul;
 }
 
 // --------------------------------------------------------------------------------------------------------

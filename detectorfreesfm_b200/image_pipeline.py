@@ -154,6 +154,43 @@ class GpuImageReader:
                                                        ctypes.c_void_p(st)))
         return out
 
+    def resize_rgb(self, image_u8, size):
+        """uint8 (H, W, 3) RGB numpy array or tensor -> CUDA float32 (3, h_new, w_new) = PIL-LANCZOS(image) / 255.
+        Pillow resamples the bands of an RGB image independently with the same coefficient tables (Resample.c, 8bpc, bands == 3), so
+        three passes of the grayscale kernel over the de-interleaved planes are bit-identical to PIL's result."""
+        if isinstance(image_u8, np.ndarray):
+            assert image_u8.dtype == np.uint8 and image_u8.ndim == 3 and image_u8.shape[2] == 3
+            h, w = image_u8.shape[:2]
+            img = self._stage(np.ascontiguousarray(image_u8).reshape(h, w * 3)).view(h, w, 3)
+        else:
+            assert image_u8.dtype == torch.uint8 and image_u8.dim() == 3 and image_u8.shape[2] == 3
+            img = image_u8.to(self.device)
+        planes = img.permute(2, 0, 1).contiguous()
+        return torch.stack([self.resize_gray(planes[c], size) for c in range(3)], 0)
+
+    def read_rgb(self, path, resize=None, resize_no_larger_than=False, df=None, pad_to=None, ret_scales=False):
+        """src/dataset/utils.py:80-118 (client=None, augmentor=None; the loader of the refinement stage,
+        src/dataset/coarse_sfm_refinement_dataset.py:365-380): image [3,h,w] float32 in [0,1] on the GPU (+ scales, original_hw)."""
+        import cv2
+        resize = tuple(resize) if resize is not None else None
+        image = cv2.imread(str(path), cv2.IMREAD_COLOR)
+        if image is None:
+            raise FileNotFoundError(f"Problem exists when loading image: {path}")
+        image = cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
+        w, h = image.shape[1], image.shape[0]
+        w_new, h_new = process_resize(w, h, resize if resize is not None else (w, h), df, resize_no_larger_than=resize_no_larger_than)
+        scales = torch.tensor([float(h) / float(h_new), float(w) / float(w_new)])
+        original_hw = torch.tensor([h, w])
+        img = self.resize_rgb(image, (w_new, h_new))
+        if pad_to is not None:
+            if pad_to == -1:
+                pad_to = max(w_new, h_new)
+            assert pad_to >= max(h_new, w_new)
+            padded = torch.zeros((3, pad_to, pad_to), dtype=torch.float32, device=self.device)
+            padded[:, :h_new, :w_new] = img
+            img = padded
+        return [img, scales, original_hw] if ret_scales else img
+
     def read_grayscale(self, path, resize=None, resize_no_larger_than=False, df=None, pad_to=None, ret_scales=False, ret_pad_mask=False):
         """src/dataset/utils.py:121-159 (client=None, augmentor=None): image [1,h,w] float32 on the GPU (+ scales, original_hw)."""
         import cv2

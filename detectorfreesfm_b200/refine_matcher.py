@@ -97,30 +97,42 @@ class B200MultiviewMatcher(torch.nn.Module):
         Hs = np.asarray([im.shape[1] for im in images], dtype=np.int32)
         Ws = np.asarray([im.shape[2] for im in images], dtype=np.int32)
 
-        def host(t, dtype):
-            return np.ascontiguousarray(t.detach().cpu().numpy().astype(dtype, copy=False))
-
-        q_idx = host(data["query_img_idxs"][0], np.int32)
-        M = q_idx.shape[0]
-        scales = host(data["scales"][0], np.float32) if "scales" in data else np.ones((n_img, 2), np.float32)
-        qpts = host(data["query_points"][0], np.float32)
-        rpts = host(data["reference_points_coarse"][0], np.float32)
-        Nq = rpts.shape[0]
-        valid = host(data["track_valid_mask"][0], np.uint8)
-        r_idx = host(data["reference_img_idxs"][0], np.int32)
-        movable = host(data["query_movable_mask"][0], np.uint8) if "query_movable_mask" in data else np.ones(M, np.uint8)
-        out_q = np.zeros((M, 2), np.float32)
-        out_r = np.zeros((Nq, M, 2), np.float32)
-        out_s = np.zeros((Nq, M), np.float32)
+        # The C ABI takes the small per-track arrays as HOST arrays (it builds the patch records on the host).  The reference worker hands
+        # the whole dict over as CUDA tensors (dict_to_cuda, multiview_match_worker.py:127): pack them into ONE float32 buffer on the
+        # device and read it back with a single copy (image indices <= 16 and the masks are exact in float32); CPU tensors are used as
+        # they are.  The three outputs stay on the device.
+        q_idx_t = data["query_img_idxs"][0]
+        M = int(q_idx_t.shape[0])
+        rpts_t = data["reference_points_coarse"][0]
+        Nq = int(rpts_t.shape[0])
+        parts = [data["scales"][0] if "scales" in data else torch.ones(n_img, 2), data["query_points"][0], rpts_t, data["track_valid_mask"][0],
+                 q_idx_t, data["reference_img_idxs"][0],
+                 data["query_movable_mask"][0] if "query_movable_mask" in data else torch.ones(M, dtype=torch.bool)]
+        sizes = [p.numel() for p in parts]
+        if any(p.is_cuda for p in parts):
+            flat = torch.cat([p.reshape(-1).to(device=dev, dtype=torch.float32) for p in parts]).cpu().numpy()
+        else:
+            flat = torch.cat([p.reshape(-1).to(torch.float32) for p in parts]).numpy()
+        offs = np.cumsum([0] + sizes)
+        seg = [flat[offs[i]:offs[i + 1]] for i in range(len(parts))]
+        scales = np.ascontiguousarray(seg[0], dtype=np.float32)
+        qpts = np.ascontiguousarray(seg[1], dtype=np.float32)
+        rpts = np.ascontiguousarray(seg[2], dtype=np.float32)
+        valid = np.ascontiguousarray(seg[3] != 0, dtype=np.uint8)
+        q_idx = np.ascontiguousarray(np.rint(seg[4]), dtype=np.int32)
+        r_idx = np.ascontiguousarray(np.rint(seg[5]), dtype=np.int32)
+        movable = np.ascontiguousarray(seg[6] != 0, dtype=np.uint8)
+        out_q = torch.zeros((1, M, 2), dtype=torch.float32, device=dev)
+        out_r = torch.zeros((1, Nq, M, 2), dtype=torch.float32, device=dev)
+        out_s = torch.zeros((1, Nq, M), dtype=torch.float32, device=dev)
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
         with torch.cuda.device(dev):
             _lib.check(self._lib.dfsfm_refine_chunk(self._h, n_img, ctypes.cast(ptrs, ctypes.c_void_p), p(Hs), p(Ws), p(scales), M, Nq, p(qpts),
-                                                    p(rpts), p(valid), p(q_idx), p(r_idx), p(movable), p(out_q), p(out_r), p(out_s),
-                                                    _lib.stream_ptr(dev)))
+                                                    p(rpts), p(valid), p(q_idx), p(r_idx), p(movable), _lib.ptr(out_q), _lib.ptr(out_r),
+                                                    _lib.ptr(out_s), _lib.stream_ptr(dev)))
         data["W"] = self.W
-        data["query_points_refined"] = torch.from_numpy(out_q)[None].to(dev)
-        rr = torch.from_numpy(out_r)[None].to(dev)
-        ss = torch.from_numpy(out_s)[None].to(dev)
+        data["query_points_refined"] = out_q
+        rr, ss = out_r, out_s
         if "reference_points_refined" in data:
             data["reference_points_refined"].append(rr)
             data["std"].append(ss)

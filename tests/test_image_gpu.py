@@ -91,3 +91,21 @@ def test_dataset_mirror_caches_and_feeds_the_matcher(tmp_path):
     assert ds2.decodes == 3 and torch.equal(ds2[0]["image0"].cpu(), io.read_grayscale_from_array(imgs[1], (128,), df=8)[0])
     with pytest.raises(NotImplementedError):
         B200CoarseMatchingDataset(dict(args, img_type="rgb"), paths, pairs, subset_ids=[0])
+
+
+@pytest.mark.parametrize("H,W,resize,df", [(150, 200, (96,), 8), (97, 61, (128,), 8), (300, 420, (256,), 8), (64, 80, None, None)])
+def test_read_rgb_matches_pil_rgb_resample(reader, tmp_path, H, W, resize, df):
+    """HP-2's loader (src/dataset/utils.py:80-118, called with resize_no_larger_than=True at coarse_sfm_refinement_dataset.py:372-380):
+    cv2 decode -> RGB -> PIL LANCZOS on the 3-band image -> /255 -> [3,h,w]; the GPU path runs the grayscale kernel per band."""
+    import cv2
+    from PIL import Image
+    from detectorfreesfm_b200.image_pipeline import process_resize
+    rgb = np.stack([util.synth_photo(H, W, seed=H + W + c) for c in range(3)], -1)
+    path = str(tmp_path / "rgb.png")
+    assert cv2.imwrite(path, cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+    t, scales, hw = reader.read_rgb(path, resize, resize_no_larger_than=True, df=df, ret_scales=True)
+    w_new, h_new = process_resize(W, H, resize if resize is not None else (W, H), df, resize_no_larger_than=True)
+    ref = np.asarray(Image.fromarray(rgb).resize((w_new, h_new), resample=Image.LANCZOS), dtype=np.uint8).astype("float32")
+    ref = torch.from_numpy(ref / 255.).float().permute(2, 0, 1).contiguous()
+    assert t.is_cuda and t.shape == ref.shape and torch.equal(t.cpu(), ref)
+    assert torch.equal(scales, torch.tensor([float(H) / float(h_new), float(W) / float(w_new)])) and torch.equal(hw, torch.tensor([H, W]))
