@@ -202,6 +202,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "1")),
+                    help="concurrent pair workers per GPU, each with its own matcher (engine handle + workspaces) and CUDA stream -- the reference "
+                         "deploys two Ray workers per GPU (n_gpus_per_worker: 0.5, src/coarse_match/coarse_match.py:53)")
     ap.add_argument("--hp2-tracks", type=int, default=2000)
     ap.add_argument("--skip-hp2", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -238,16 +241,50 @@ def main():
         m_stats["counts"] = counts[1:].tolist()
         return merger.merge(torch.cat(out, 0), torch.cumsum(counts, 0), pair_img, N_IMAGES)
 
+    # optional: several pair workers per GPU (threads; the C ABI calls and the per-pair count read-back release the GIL).  One pair at a time
+    # offers only 43 / 86 CTA-pair tiles per encoder launch to 74 CTA pairs; two independent pairs in flight fill the gaps.
+    n_workers = max(1, args.workers_per_gpu)
+    workers = [(matcher, torch.cuda.current_stream(dev))]
+    for _ in range(1, n_workers):
+        mw = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=2 * N_IMAGES).cuda(local).eval()
+        mw.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
+        workers.append((mw, torch.cuda.Stream(device=dev)))
+
+    def run_pairs(widx, todo, cached, out):
+        mw, stream = workers[widx]
+        torch.cuda.set_device(local)
+        with torch.cuda.stream(stream):
+            for k in todo:
+                i, j = pairs[k]
+                data = {"image0": dev_images[i], "image1": dev_images[j], "scale0": ones, "scale1": ones}
+                if cached:
+                    data["pair_key"] = ((f"im{i}",), (f"im{j}",))
+                mw(data)
+                out[k] = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
+
     def step_resident(cached):
         """inputs resident in HBM; returns the per-pair (M,5) device arrays"""
-        matcher._cache.clear()
-        out = []
-        for (i, j) in pairs:
-            data = {"image0": dev_images[i], "image1": dev_images[j], "scale0": ones, "scale1": ones}
-            if cached:
-                data["pair_key"] = ((f"im{i}",), (f"im{j}",))
-            matcher(data)
-            out.append(torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1))
+        out = [None] * len(pairs)
+        for mw, _ in workers:
+            mw._cache.clear()
+        if n_workers == 1:
+            run_pairs(0, range(len(pairs)), cached, out)
+        else:
+            main = torch.cuda.current_stream(dev)
+            start = torch.cuda.Event()
+            start.record(main)
+            ths = []
+            for w in range(1, n_workers):
+                workers[w][1].wait_event(start)
+                ths.append(threading.Thread(target=run_pairs, args=(w, range(w, len(pairs), n_workers), cached, out)))
+                ths[-1].start()
+            run_pairs(0, range(0, len(pairs), n_workers), cached, out)
+            for t in ths:
+                t.join()
+            for w in range(1, n_workers):
+                done = torch.cuda.Event()
+                done.record(workers[w][1])
+                main.wait_event(done)
         m_stats["merged"] = merge_step(out)
         return out
 
@@ -326,6 +363,24 @@ def main():
                         "(split-fp16 operands for fp32-grade parity): `executed` = 3 x achieved is the fp16 tensor-pipe rate (padding and halo rows not counted)",
                 "launches": conv_cnt, "avg_launch_ms": conv_ms / conv_cnt if conv_cnt else None, "share_of_step": conv_ms / total_ms if total_ms else None,
                 "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof.items())}}
+
+    # the kernel north_star sets the 70 % target for: the LoFTR encoder layer (1.343 MFLOP per token per layer call)
+    enc_keys = ("lin", "kv", "kv_final", "attn", "fold", "kvproj", "enc_fused")
+    enc_ms = sum(prof[k][1] for k in enc_keys if k in prof)
+    L_tok = (HW // 8) ** 2
+    enc_alg = 16 * L_tok * 1.343e6 * len(pairs)
+    enc_tiles = 4 * (2 * ((L_tok + 255) // 256)) + 8 * ((L_tok + 255) // 256)        # 256-token CTA-pair tiles per pair: 4 self + 8 cross calls
+    enc_rounds = 4 * -(-(2 * ((L_tok + 255) // 256)) // 74) + 8 * -(-((L_tok + 255) // 256) // 74)
+    roofline_encoder = {
+        "bound": "tensor", "kernel": "LoFTR encoder layer: KvEpi k/v projection + state reduction, kvp_fold, enc256_fused_kernel (or the GEMM-per-linear schedule)",
+        "achieved": enc_alg / (enc_ms * 1e-3) / 1e12 if enc_ms else None, "peak": peaks["tflops"], "unit": "TFLOP/s",
+        "frac": enc_alg / (enc_ms * 1e-3) / 1e12 / peaks["tflops"] if enc_ms else None, "passes": 3,
+        "executed_frac": 3 * enc_alg / (enc_ms * 1e-3) / 1e12 / peaks["tflops"] if enc_ms else None,
+        "ms_per_step": enc_ms, "kernels": {k: round(prof[k][1], 3) for k in enc_keys if k in prof},
+        "tile_occupancy": enc_tiles / (enc_rounds * 74.0),
+        "note": "algorithmic = 1.343 MFLOP/token/layer-call x 16 calls x 10816 tokens per pair; 3 fp16 passes executed (split-fp16); one pair at a "
+                "time gives 43 (cross) / 86 (self) 256-token tiles per launch for 74 CTA pairs: tile_occupancy is the resulting upper bound on SM use"}
+    roofline["encoder_layer"] = roofline_encoder
 
     # ------------------------------------------------------------------ HP-2: one refinement chunk (C3)
     hp2 = None
@@ -520,7 +575,8 @@ def main():
             "config": {"workload": WORKLOAD,
                        "l2": "per-step working set (activations of one 832x832 image ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "backbone": "run for both images of every pair in `value`/`e2e` (as the reference does); *_cached keys use the exact per-image feature cache",
-                       "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays"},
+                       "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays",
+                       "pair_workers_per_gpu": n_workers},
             "value_cached": n_pairs * K / (ms_cached * 1e-3),
             "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "value_cached": n_pairs * K / (ms_e2e_cached * 1e-3)},

@@ -150,7 +150,7 @@ static bool enc_fused() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DFSFM_ENC_FUSED");
-        v = (e && e[0] == '1') ? 1 : 0;   // opt-in until validated on hardware
+        v = (e && e[0] == '0') ? 0 : 1;
     }
     return v == 1;
 }
@@ -480,7 +480,7 @@ void CoarseEngine::layer_call(int li, bool self, int x0, int xn, int s0, int sn,
         // (3) partial states -> V/len -> G = KV . Wm^T and Ksum, in one kernel
         { const HL& wm = params.mat(p + ".merge");
           LaunchScope ls("fold", st);
-          kvp_fold_kernel<<<dim3(8, n_segs), 1024, 0, st>>>(tok_.kvp_part, tok_.kvp_flags, ke.epoch, n_ctas, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(),
+          kvp_fold_kernel<<<dim3(8, 8, n_segs), 1024, 0, st>>>(tok_.kvp_part, tok_.kvp_flags, ke.epoch, n_ctas, tok_.seg_dev + kv_seg0, wm.hi, wm.lo(),
                                                          tok_.g.hi, tok_.g.lo(), tok_.ksum); }
         DFSFM_CUDA(cudaGetLastError());
     }

@@ -50,7 +50,17 @@ struct EncParams {
     const float* ln1_g;
     const float* ln1_b;
     LinEpiParams e4;       // LayerNorm2 + residual + stores (M, N = 256, gamma/beta, res_hi/lo, out_hi/lo[, out_f32])
+    unsigned long long* tl;  // debugging: when set, [CTA][16] globaltimer stamps (dfsfm_debug_timeline): 0 entry, 1 set-up done, 2 dependency
+                             //   wait over, 3 first x chunk landed, 4 GEMM1 issued; first tile, epilogue warp 2: 5/6 E1 begin/end, 7/8 E2, 9 E3(0)
+                             //   begin, 10 E3(1) end, 12/13 E4 begin/end; 14 last tile done, 11 exit
 };
+__device__ __forceinline__ void enc_stamp(const EncParams& p, int ev) {
+    if (p.tl != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.tl[blockIdx.x * 16 + ev] = t;
+    }
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
     asm volatile(
@@ -100,6 +110,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     float* lnx = reinterpret_cast<float*>(smem + kEncLnxOff);
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) enc_stamp(p, 0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -120,7 +131,9 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) enc_stamp(p, 1);
     asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 0) enc_stamp(p, 2);
     constexpr uint32_t R0 = 0, R1 = 256;
 
     if (warp == 0) {
@@ -207,10 +220,12 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 for (int c = 0; c < 4; ++c) {
                     mbar_wait(&x_full[c], tp);
                     const uint32_t b = ring_wait();
+                    if (first && c == 0) enc_stamp(p, 3);
                     mma_ss(R0, act_a + c * kEncChunk, b, c == 0);
                     ring_release(b);
                 }
                 umma_commit_2sm(q_done);
+                if (first) enc_stamp(p, 4);
                 // ---- GEMM2: acc_mg (R1) = (Q*Z)[TMEM R0] . G^T   (R1 = acc_out of the previous tile until its last epilogue has read it)
                 if (!first) mbar_wait(e4_done, tp ^ 1u);
                 mbar_wait(qp_ready, tp);
@@ -268,8 +283,10 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             const int seg = (p.seg_tile0 > 0 && tile >= p.seg_tile0) ? 1 : 0;
             const int row0 = (tile * 2 + static_cast<int>(rank)) * kBM + quad * 32;
             // ---- E1: q -> Q*Z, packed in place as the A operand of the merge GEMM (four heads per warp)
+            const bool stamp = warp == 2 && lane == 0 && tile == cluster_id;
             mbar_wait(q_done, tp);
             tc_fence_after();
+            if (stamp) enc_stamp(p, 5);
 #pragma unroll 1
             for (int b = 0; b < 4; ++b) {
                 float v[32];
@@ -297,9 +314,11 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(qp_ready, 0);
+            if (stamp) enc_stamp(p, 6);
             // ---- E2: LayerNorm1(acc_mg) -> m, written to act as the (hi, lo) A operand of mlp.0's second half
             mbar_wait(mg_done, tp);
             tc_fence_after();
+            if (stamp) enc_stamp(p, 7);
             {
                 float v[128];
 #pragma unroll
@@ -342,11 +361,13 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(m_ready, 0);
+            if (stamp) enc_stamp(p, 8);
             // ---- E3: relu(hid chunk) packed in place as the A operand of mlp.2
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
                 mbar_wait(&h_done[j], tp);
                 tc_fence_after();
+                if (stamp && j == 0) enc_stamp(p, 9);
 #pragma unroll 1
                 for (int b = 0; b < 4; ++b) {
                     float v[32];
@@ -362,10 +383,12 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_remote(&hid_ready[j], 0);
+                if (stamp && j == 1) enc_stamp(p, 10);
             }
             // ---- E4: x + LayerNorm2(acc_out) -> HBM (split planes [+ fp32]); the 32x32 store transposition is staged in act chunk 3
             mbar_wait(out_done, tp);
             tc_fence_after();
+            if (stamp) enc_stamp(p, 12);
             {
                 EpiCtx ctx;
                 ctx.stg = act + 3 * kEncChunk + (warp - 2) * 4096;
@@ -376,11 +399,14 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive_remote(e4_done, 0); mbar_arrive_remote(e4_done, 1); }
+            if (stamp) enc_stamp(p, 13);
+            if (warp == 2 && lane == 0) enc_stamp(p, 14);
             tp ^= 1u;
         }
     }
     tc_fence_before();
     cluster_sync_all();
+    if (threadIdx.x == 0) enc_stamp(p, 11);
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc_2sm<512>(tmem_base);

@@ -133,6 +133,7 @@ inline void launch_enc256_fused(const HL& x, long long row0, long long T, const 
     const int tiles = static_cast<int>((T + 2 * kBM - 1) / (2 * kBM));
     const int max_clusters = sm_count() / 2;
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    p.tl = timeline_next_launch(2 * clusters, tiles);
     LaunchScope ls("enc_fused", st);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

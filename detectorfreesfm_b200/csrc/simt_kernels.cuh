@@ -365,42 +365,45 @@ static __global__ void __launch_bounds__(8 * D) attn_fold_merge_kernel(const flo
     }
 }
 
-// The same fold fed directly by the per-CTA partial states of KvEpi: one kernel sums the partials of its head in CTA order
-// (deterministic), applies V's 1/len, and writes G and Ksum -- the state itself never goes back to HBM.
-// grid (8 heads, launch segments), block 1024 = 4 CTA groups x 256 (sum) / 4 d-groups x 256 output channels (fold).
+// The same fold fed directly by the per-CTA partial states of KvEpi: one kernel sums the partials in CTA order (deterministic),
+// applies V's 1/len, and writes G and Ksum -- the state itself never goes back to HBM.  Latency-bound (5 MB of partials per segment,
+// a chain of dependent loads per thread), hence spread wide: grid (8 heads, 8 d-slices of 4 rows, launch segments) = 128 blocks for a
+// pair, block 1024 = 7 CTA groups x 132 state elements for the sum, then 256 output channels x 4 d rows for the fold.
 static __global__ void __launch_bounds__(1024) kvp_fold_kernel(const float* __restrict__ part, const unsigned* __restrict__ flags, unsigned epoch,
                                                                int n_ctas, const Seg* __restrict__ segs, const __half* __restrict__ wm_hi,
                                                                const __half* __restrict__ wm_lo, __half* __restrict__ g_hi, __half* __restrict__ g_lo,
                                                                float* __restrict__ ksum_out) {
-    constexpr int D = 32, C = 256, HS = D * (D + 1), PF = 4 * HS;
-    __shared__ float red[4][HS];
-    __shared__ float kv[D][D + 1];
+    constexpr int D = 32, C = 256, HS = D * (D + 1), PF = 4 * HS, E = 4 * (D + 1), G = 7;
+    __shared__ float red[G][E];
+    __shared__ float kv[4][D + 1];
     __shared__ unsigned char ok[160];
-    const int h = blockIdx.x, seg = blockIdx.y, tid = threadIdx.x;
+    const int h = blockIdx.x, ds = blockIdx.y, seg = blockIdx.z, tid = threadIdx.x;
     const Seg sg = segs[seg];
     const int nt = h >> 2, hh = h & 3;
     const long long slot0 = static_cast<long long>(seg * 2 + nt) * n_ctas;
     for (int c = tid; c < n_ctas; c += 1024) ok[c] = flags[slot0 + c] == epoch;
     __syncthreads();
-    const int grp = tid >> 8, t = tid & 255;
-    const float* base = part + slot0 * PF + hh * HS;
-    for (int e = t; e < HS; e += 256) {
+    const int grp = tid / E, e = tid - grp * E;
+    if (grp < G) {
+        const float* base = part + slot0 * PF + hh * HS + ds * E + e;   // rows d = 4*ds .. 4*ds+3 of head h: E consecutive floats
         float s = 0.f;
 #pragma unroll 8
-        for (int c = grp; c < n_ctas; c += 4)
-            if (ok[c]) s += base[static_cast<long long>(c) * PF + e];
+        for (int c = grp; c < n_ctas; c += G)
+            if (ok[c]) s += base[static_cast<long long>(c) * PF];
         red[grp][e] = s;
     }
     __syncthreads();
-    const float inv_len = 1.f / static_cast<float>(sg.count);
-    for (int e = tid; e < HS; e += 1024) {
-        const float v = (red[0][e] + red[1][e]) + (red[2][e] + red[3][e]);
-        (&kv[0][0])[e] = (e % (D + 1)) < D ? v * inv_len : v;
+    if (tid < E) {
+        float v = red[0][tid];
+#pragma unroll
+        for (int g = 1; g < G; ++g) v += red[g][tid];
+        (&kv[0][0])[tid] = (tid % (D + 1)) < D ? v / static_cast<float>(sg.count) : v;
     }
     __syncthreads();
-    if (tid < D) ksum_out[seg * C + h * D + tid] = kv[tid][D];
-    const int n = t, d0 = grp * 8;
-    float w[D];
+    if (tid < 4) ksum_out[seg * C + h * D + ds * 4 + tid] = kv[tid][D];
+    if (tid >= C) return;
+    const int n = tid;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int v = 0; v < D; v += 8) {
         const uint4 uh = *reinterpret_cast<const uint4*>(wm_hi + static_cast<long long>(n) * C + h * D + v);
@@ -409,27 +412,18 @@ static __global__ void __launch_bounds__(1024) kvp_fold_kernel(const float* __re
         const __half2* pl = reinterpret_cast<const __half2*>(&ul);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 a = __half22float2(ph[q]), b = __half22float2(pl[q]);
-            w[v + 2 * q] = a.x + b.x;
-            w[v + 2 * q + 1] = a.y + b.y;
+            const float2 x = __half22float2(ph[q]), y = __half22float2(pl[q]);
+            const float w0 = x.x + y.x, w1 = x.y + y.y;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) a[d] = fmaf(kv[d][v + 2 * q + 1], w1, fmaf(kv[d][v + 2 * q], w0, a[d]));
         }
     }
-    uint4 uh, ul;
-    uint32_t* oh = reinterpret_cast<uint32_t*>(&uh);
-    uint32_t* ol = reinterpret_cast<uint32_t*>(&ul);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int v = 0; v < D; ++v) {
-            a0 = fmaf(kv[d0 + 2 * q][v], w[v], a0);
-            a1 = fmaf(kv[d0 + 2 * q + 1][v], w[v], a1);
-        }
-        split_f16x2(a0, a1, oh[q], ol[q]);
-    }
-    const long long o = (static_cast<long long>(seg) * C + n) * C + h * D + d0;
-    *reinterpret_cast<uint4*>(g_hi + o) = uh;
-    *reinterpret_cast<uint4*>(g_lo + o) = ul;
+    uint2 uh2, ul2;
+    split_f16x2(a[0], a[1], uh2.x, ul2.x);
+    split_f16x2(a[2], a[3], uh2.y, ul2.y);
+    const long long o = (static_cast<long long>(seg) * C + n) * C + h * D + ds * 4;
+    *reinterpret_cast<uint2*>(g_hi + o) = uh2;
+    *reinterpret_cast<uint2*>(g_lo + o) = ul2;
 }
 
 // --------------------------------------------------------------------------------------------------------

@@ -10,9 +10,10 @@ from tests import util
 first = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 count = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 lib = _lib.load_library()
+raw = len(sys.argv) > 3 and sys.argv[3] == "raw"   # raw: medians (and max) of all 16 stamps of every launch
 m = B200LoFTR(util.loftr_config()).cuda().eval()
-m.load_state_dict(weights.loftr_state_dict(0))
-ims = [util.synth_image(832, 832, 1000 + i).cuda() for i in range(2)]
+m.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
+ims = [im.cuda() for im in util.synth_scene(2, 832, 832, 1000, noise=0.025)[0]]
 for _ in range(2):
     m({"image0": ims[0], "image1": ims[1]})
 torch.cuda.synchronize()
@@ -43,6 +44,10 @@ for i in range(first, min(n, first + count)):
         if not ok.any(): return float("nan")
         return float((v[ok] - t0).max()) / 1e3
     gap = "" if prev_end is None else f" gap_prev_end->start {(t0 - prev_end) / 1e3:6.1f}"
+    if raw:
+        print(f"{i:3d} {c:4d} {tiles:5d} | " + " ".join(f"e{ev}:{med(ev):5.1f}/{mx(ev):5.1f}" for ev in range(1, 16)) + gap)
+        prev_end = s[:, 11].max()
+        continue
     print(f"{i:3d} {c:4d} {tiles:5d} | {mx(11):6.1f} | e1 {med(1):5.1f} e2 {med(2):5.1f} e3 {med(3, arr=lead):5.1f} e4 {med(4, arr=lead):5.1f} e6 {med(6):5.1f} e7 {med(7):5.1f} |"
           f" e5 {mx(5, arr=lead):5.1f} e8 {mx(8):5.1f} e9 {mx(9):5.1f} | e10 {mx(10):5.1f} e11 {mx(11):5.1f}{gap}")
     prev_end = s[:, 11].max()
