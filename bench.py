@@ -195,6 +195,124 @@ def hp2_cpu_baseline(n_sub):
 
 
 
+# ------------------------------------------------------------------------------ BASELINE configs[3] / configs[4]: sharded scenes
+def _timed_region(fn, steps, dev, D):
+    D.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    D.barrier()
+    return D.max_over_ranks(e0.elapsed_time(e1), dev), out
+
+
+def run_c4(args):
+    """C4: one scene of --c4-images overlapping 832x832 views, EXHAUSTIVE pairs (101 -> 5050), strong scaling: the pair list is dealt
+    to the ranks by image locality (dist.shard_pairs_by_image), every rank matches its pairs with the per-image feature cache, the
+    match -> keypoint merge runs sharded by image owner (postprocess_dist.merge_keypoints_sharded: one all_to_all of [x,y,conf] rows and
+    one of the ids over NCCL), and only rank 0 receives the per-pair keypoint-id arrays (gather_varlen_to)."""
+    from detectorfreesfm_b200 import B200LoFTR
+    from detectorfreesfm_b200 import dist as D
+    from detectorfreesfm_b200.postprocess_dist import merge_keypoints_sharded
+    from tests import weights
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_img = args.c4_images
+    names = [f"scene/img_{i:04d}.jpg" for i in range(n_img)]
+    pairs = list(itertools.combinations(range(n_img), 2))
+    mine = D.shard_pairs_by_image(pairs, rank, world)
+    images = util.synth_scene(n_img, HW, HW, 77, noise=NOISE, max_shift=256)[0]          # same scene on every rank (seeded)
+    touched = sorted({i for k in mine for i in pairs[k]})
+    dev_images = {i: images[i].to(dev) for i in touched}
+    matcher = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=n_img + 1).cuda(local).eval()
+    matcher.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
+    ones = torch.ones(1, 2, device=dev)
+    stats = {}
+
+    def step():
+        matcher.clear_cache()
+        local_matches = {}
+        for k in mine:
+            i, j = pairs[k]
+            data = {"image0": dev_images[i], "image1": dev_images[j], "scale0": ones, "scale1": ones, "pair_key": ((names[i],), (names[j],))}
+            matcher(data)
+            local_matches[f"{names[i]} {names[j]}"] = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
+        fk, fs, upd = merge_keypoints_sharded(local_matches, mine, names, " ", device=dev)
+        ids = [torch.from_numpy(upd[k].astype(np.float32)).to(dev) for k in local_matches]
+        got = D.gather_varlen_to(ids, dst=0)
+        stats["matches"] = int(sum(v.shape[0] for v in local_matches.values()))
+        stats["keypoints"] = int(sum(v.shape[0] for v in fk.values()))
+        stats["gathered_pairs"] = None if got is None else sum(len(g) for g in got)
+        return got
+
+    W, K = max(1, min(args.warmup, 1)), max(1, min(args.steps, 2))
+    for _ in range(W):
+        step()
+    ms, _ = _timed_region(step, K, dev, D)
+    total_matches = int(D.sum_over_ranks(stats["matches"], dev))
+    pairs_max = int(D.max_over_ranks(len(mine), dev))
+    if rank == 0:
+        print(json.dumps({
+            "metric": "image-pairs/s coarse-match, C4 full pair graph", "value": len(pairs) * K / (ms * 1e-3), "unit": "pairs/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16x2-split (fp32-grade), fp32 accumulate", "data": "synthetic",
+            "config": {"workload": f"C4: {n_img} overlapping synthetic {HW}x{HW} views, exhaustive {len(pairs)} pairs sharded by image locality over "
+                                   f"{world} rank(s), per-image feature cache, sharded keypoint merge over NCCL, ids gathered to rank 0",
+                       "pairs_on_slowest_rank": pairs_max, "matches_total": total_matches, "keypoints": stats["keypoints"],
+                       "gathered_pairs_on_rank0": stats["gathered_pairs"]}}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def run_c5(args):
+    """C5: --c5-chunks refinement chunks of 2000 tracks (500 -> 1e6 tracks) dealt round-robin to the ranks (chunks never interact;
+    dist.shard), every chunk dict travelling host -> device and its refined points back, [K,4]-sized results gathered to rank 0."""
+    from detectorfreesfm_b200 import B200MultiviewMatcher
+    from detectorfreesfm_b200 import dist as D
+    from tests import weights
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rm = B200MultiviewMatcher(util.multiview_config(15, 7), test=True).cuda(local).eval()
+    rm.load_state_dict(weights.multiview_state_dict(0))
+    mine = D.shard(args.c5_chunks, rank, world)
+    pool = [hp2_chunk(2000, 100 + s) for s in range(4)]                                 # 4 distinct synthetic chunks, reused cyclically
+    pool = [{k: ([im.pin_memory() for im in v] if isinstance(v, list) else (v.pin_memory() if torch.is_tensor(v) else v)) for k, v in c.items()}
+            for c in pool]
+
+    def step():
+        res = []
+        for c in mine:
+            h = pool[c % len(pool)]
+            d = {k: ([im.to(dev, non_blocking=True) for im in v] if isinstance(v, list) else (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v))
+                 for k, v in h.items()}
+            rm(d)
+            mask = d["track_valid_mask"][0]
+            res.append(torch.cat([d["query_points_refined"][0], d["reference_points_refined"][-1][0][mask]], 0))   # the [K,2] part of matchWorker's rows
+        return D.gather_varlen_to(res, dst=0)
+
+    step_small = mine[:2]
+    for _ in range(1):                                                                   # warm-up on two chunks
+        saved, mine[:] = list(mine), step_small
+        step()
+        mine[:] = saved
+    ms, _ = _timed_region(step, 1, dev, D)
+    tracks = args.c5_chunks * 2000
+    if rank == 0:
+        print(json.dumps({
+            "metric": "tracks/s refinement, C5 chunks sharded", "value": tracks / (ms * 1e-3), "unit": "tracks/s", "n_gpus": world, "steps": 1,
+            "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16x2-split (fp32-grade), fp32 accumulate", "data": "synthetic",
+            "config": {"workload": f"C5: {args.c5_chunks} chunks x 2000 tracks ({tracks} tracks, <= 9 query views, 10 images of 600x800 per chunk) "
+                                   f"round-robin over {world} rank(s), host chunk dict -> device per chunk, refined points gathered to rank 0"}}))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 # ----------------------------------------------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -205,6 +323,11 @@ def main():
     ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "1")),
                     help="concurrent pair workers per GPU, each with its own matcher (engine handle + workspaces) and CUDA stream -- the reference "
                          "deploys two Ray workers per GPU (n_gpus_per_worker: 0.5, src/coarse_match/coarse_match.py:53)")
+    ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
+                    help="c2 (default): the headline line, one demo scene per rank; c4: IMC-style full pair graph (5050 pairs of 101 images) sharded "
+                         "over the ranks, strong scaling; c5: Bridge-scale refinement, --c5-chunks chunks of 2000 tracks sharded over the ranks")
+    ap.add_argument("--c4-images", type=int, default=101)
+    ap.add_argument("--c5-chunks", type=int, default=500)
     ap.add_argument("--hp2-tracks", type=int, default=2000)
     ap.add_argument("--skip-hp2", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
@@ -213,6 +336,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "c4":
+        return run_c4(args)
+    if args.config == "c5":
+        return run_c5(args)
 
     from detectorfreesfm_b200 import B200LoFTR, B200MultiviewMatcher, KeypointMerger, _lib
     from detectorfreesfm_b200 import dist as D

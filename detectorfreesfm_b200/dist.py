@@ -68,6 +68,56 @@ def gather_varlen(local, dst=0):
     return out
 
 
+def gather_varlen_to(local, dst=0):
+    """Like gather_varlen, but nothing travels to the ranks that do not need it: the per-unit row counts are all-gathered (a few
+    hundred bytes), then every rank sends ONE packed [rows, C] buffer of its exact size to ``dst`` (point-to-point over NCCL / gloo).
+    Returns on dst: list (rank order) of lists of tensors; elsewhere: None."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return [list(local)]
+    world, rank = dist.get_world_size(), dist.get_rank()
+    nccl = dist.get_backend() == "nccl"
+    dev = local[0].device if len(local) else (torch.device("cuda", torch.cuda.current_device()) if nccl else torch.device("cpu"))
+    C = local[0].shape[1] if len(local) else 0
+    counts = [int(t.shape[0]) for t in local]
+    metas = [None] * world
+    dist.all_gather_object(metas, (C, counts))
+    C = max(m[0] for m in metas)
+    if rank != dst:
+        if sum(counts) > 0:
+            dist.send(torch.cat([t.to(torch.float32) for t in local], 0).contiguous(), dst)
+        return None
+    out = []
+    for r in range(world):
+        rows = metas[r][1]
+        if r == rank:
+            out.append([t.to(torch.float32) for t in local])
+            continue
+        total = sum(rows)
+        buf = torch.empty((total, C), dtype=torch.float32, device=dev)
+        if total > 0:
+            dist.recv(buf, r)
+        out.append(list(torch.split(buf, rows)) if rows else [])
+    return out
+
+
+def shard_pairs_by_image(pairs, rank, world):
+    """Locality-aware partition of a pair list: pairs are grouped by their FIRST image and the groups are dealt to the ranks
+    as contiguous image ranges of (nearly) equal pair count, so that a rank's per-image feature cache sees every first image once and
+    the second images of its range once each.  -> indices into ``pairs`` owned by ``rank`` (ascending)."""
+    first = sorted({p[0] for p in pairs})
+    per_img = {i: 0 for i in first}
+    for p in pairs:
+        per_img[p[0]] += 1
+    target = len(pairs) / float(world)
+    owner, acc, r = {}, 0, 0
+    for i in first:
+        if r < world - 1 and acc >= target * (r + 1) - per_img[i] / 2.0:
+            r += 1
+        owner[i] = r
+        acc += per_img[i]
+    return [k for k, p in enumerate(pairs) if owner[p[0]] == rank]
+
+
 def barrier():
     if dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()

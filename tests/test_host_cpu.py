@@ -98,9 +98,13 @@ def _gloo_worker(rank, world, port, q):
     mine = D.shard(7, r, w)
     local = [torch.full((i + 1, 5), float(i)) for i in mine]  # unit i has i+1 rows filled with i
     got = D.gather_varlen(local)
+    got2 = D.gather_varlen_to(local + [torch.zeros((0, 5))], dst=0)       # point-to-point variant: only dst receives (incl. an empty unit)
+    assert (got2 is None) == (r != 0)
     t = D.max_over_ranks(1.0 + r, torch.device("cpu"))
     if r == 0:
         flat = sorted((int(t_[0, 0]), t_.shape[0]) for per_rank in got for t_ in per_rank)
+        flat2 = sorted((int(t_[0, 0]), t_.shape[0]) for per_rank in got2 for t_ in per_rank if t_.shape[0])
+        assert flat2 == flat and [len(x) for x in got2] == [len(x) + 1 for x in got]
         q.put((flat, t, [len(x) for x in got]))
     dist.barrier()
     dist.destroy_process_group()
@@ -142,6 +146,21 @@ def test_shard_covers_every_unit_once():
         assert seen == list(range(n))
         sizes = [len(shard(n, r, world)) for r in range(world)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_locality_partition_of_the_pair_graph():
+    """dist.shard_pairs_by_image: every pair exactly once, balanced to a few %, and a rank's first images form one contiguous range"""
+    import itertools
+    from detectorfreesfm_b200.dist import shard_pairs_by_image
+    pairs = list(itertools.combinations(range(101), 2))
+    for world in (1, 2, 4, 8):
+        parts = [shard_pairs_by_image(pairs, r, world) for r in range(world)]
+        assert sorted(k for p in parts for k in p) == list(range(len(pairs)))
+        sizes = [len(p) for p in parts]
+        assert max(sizes) <= 1.15 * len(pairs) / world + 1
+        for p in parts:
+            firsts = sorted({pairs[k][0] for k in p})
+            assert firsts == list(range(firsts[0], firsts[-1] + 1))
 
 
 def _oracle_flat_merge(rows5, pair_off, pair_img, n_images):
