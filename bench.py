@@ -391,6 +391,7 @@ def main():
 
     def step_resident(cached):
         """inputs resident in HBM; returns the per-pair (M,5) device arrays"""
+        nonlocal n_workers
         out = [None] * len(pairs)
         for mw, _ in workers:
             mw._cache.clear()
@@ -473,7 +474,9 @@ def main():
 
     # ------------------------------------------------------------------ roofline attribution of the dominant kernel
     lib.dfsfm_profile_enable(1)
+    saved_workers, n_workers = n_workers, 1       # per-kernel attribution: one pair at a time (concurrent pairs overlap their kernels)
     step_resident(False)
+    n_workers = saved_workers
     prof = profile_report(lib)
     lib.dfsfm_profile_enable(0)
     peaks = measured_peaks()

@@ -1,5 +1,7 @@
 // Library-wide state (last error, launch counter), the standalone RoIAlign op and the engine test hook.
 #include "../../include/dfsfm_b200.h"
+#include <mutex>
+
 #include "engine_common.h"
 
 namespace dfsfm {
@@ -36,6 +38,8 @@ namespace {
 struct ProfRec { std::string label; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
+std::mutex g_prof_mu;                      // several host threads may drive engines concurrently (one engine handle per thread)
+thread_local size_t g_prof_open = 0;       // index of this thread's open record
 }  // namespace
 bool profiling_enabled() { return g_prof_on; }
 void prof_begin(const char* label, cudaStream_t st) {
@@ -44,9 +48,18 @@ void prof_begin(const char* label, cudaStream_t st) {
     cudaEventCreate(&r.a);
     cudaEventCreate(&r.b);
     cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_open = g_prof.size();
     g_prof.push_back(r);
 }
-void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+void prof_end(cudaStream_t st) {
+    cudaEvent_t b;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        b = g_prof[g_prof_open].b;
+    }
+    cudaEventRecord(b, st);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // TensorFlow-style crop_and_resize forward (the reference's L0 native op):

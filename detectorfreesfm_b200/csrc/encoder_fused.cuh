@@ -80,6 +80,15 @@ __device__ __forceinline__ void umma_f16_2sm_ts(uint32_t tmem_d, uint32_t tmem_a
         "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// TMA store shared -> global (bulk async group), rows past the tensor's extent are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // 32 fp32 values of one row -> the in-place A-operand image of their 32-column block: columns [0,16) = hi halves (elements 2c, 2c+1 in
 // column c), columns [16,32) = lo halves.  K step s (16 elements) of the block reads columns 8s.. (hi) and 16+8s.. (lo).
 __device__ __forceinline__ void pack_block_hl(const float* v, uint32_t* r) {
@@ -106,7 +115,8 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     uint64_t* m_ready = bars + 18;
     uint64_t* hid_ready = bars + 19;    // [2]
     uint64_t* e4_done = bars + 21;      // epilogue warps of both CTAs -> BOTH CTAs (16 arrivals each)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* xr_full = bars + 22;      // residual x tile landed in act (per CTA, local TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
     float* lnx = reinterpret_cast<float*>(smem + kEncLnxOff);
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -124,6 +134,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
         mbar_init(out_done, 1); mbar_init(g4_done, 1); mbar_init(g3m_done, 1);
         mbar_init(qp_ready, 16); mbar_init(m_ready, 16); mbar_init(&hid_ready[0], 16); mbar_init(&hid_ready[1], 16);
         mbar_init(e4_done, 16);
+        mbar_init(xr_full, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
@@ -135,6 +146,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) enc_stamp(p, 2);
     constexpr uint32_t R0 = 0, R1 = 256;
+    const bool tma_e4 = p.e4.out_f32 == nullptr;   // the last layer also writes an fp32 copy: it keeps the register-path epilogue
 
     if (warp == 0) {
         // ===================================================================================== TMA producer (one thread per CTA)
@@ -155,11 +167,10 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 const int m0 = (tile * 2 + static_cast<int>(rank)) * kBM;
                 const int seg = (p.seg_tile0 > 0 && tile >= p.seg_tile0) ? 1 : 0;
                 const int wrow = static_cast<int>(rank) * 128;
-                // x tile -> act (the previous tile's m must be dead: its last readers are the m-part MMAs of mlp.0; chunk 3 is also the
-                // staging buffer of the previous tile's last epilogue), interleaved with the Wq chunks so that GEMM1 can start early
-                if (!first) mbar_wait(g3m_done, tp ^ 1u);
+                // x tile -> act (free once the previous tile's last epilogue is done with it: residual tile / store staging),
+                // interleaved with the Wq chunks so that GEMM1 can start early
+                if (!first) mbar_wait(e4_done, tp ^ 1u);
                 for (int c = 0; c < 4; ++c) {
-                    if (c == 3 && !first) mbar_wait(e4_done, tp ^ 1u);
                     if (rank == 0) mbar_arrive_expect_tx(&x_full[c], 2 * kEncChunk);
                     tma_load_3d_2sm(act + c * kEncChunk, &maps.x, &x_full[c], c * 64, m0, 0);
                     tma_load_3d_2sm(act + c * kEncChunk + 16384, &maps.x, &x_full[c], c * 64, m0, 1);
@@ -173,6 +184,16 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     }
                     for (int c = 0; c < 4; ++c) ring_load(&maps.w0, 256 + c * 64, j * 256 + wrow);
                     for (int c = 0; c < 4; ++c) ring_load(&maps.w2, j * 256 + c * 64, wrow);
+                }
+                if (tma_e4) {
+                    // the residual: this CTA's x rows once more (L2), into act as soon as mlp.0 is done reading m from it; the last
+                    // epilogue adds LayerNorm2 on top IN PLACE and the tile leaves through a TMA store
+                    mbar_wait(g3m_done, tp);
+                    mbar_arrive_expect_tx(xr_full, kEncAct);
+                    for (int c = 0; c < 4; ++c) {
+                        tma_load_3d(act + c * kEncChunk, &maps.x, xr_full, c * 64, m0, 0);
+                        tma_load_3d(act + c * kEncChunk + 16384, &maps.x, xr_full, c * 64, m0, 1);
+                    }
                 }
                 first = false;
                 tp ^= 1u;
@@ -287,28 +308,32 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             mbar_wait(q_done, tp);
             tc_fence_after();
             if (stamp) enc_stamp(p, 5);
-#pragma unroll 1
-            for (int b = 0; b < 4; ++b) {
-                float v[32];
-                tmem_ld32(tw + R0 + cb + 32 * b, v);
+            {
+                float va[128];   // all four heads of this warp in one TMEM round trip
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tmem_ld32(tw + R0 + cb + 32 * b, va + 32 * b);
                 tmem_ld_wait();
-                const float* ks = p.ksum + seg * 256 + cb + 32 * b;
-                float dot = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + j));
-                    v[j] = v[j] > 0.f ? v[j] + 1.f : fast_ex2(v[j] * 1.4426950408889634f);          // elu(x) + 1
-                    v[j + 1] = v[j + 1] > 0.f ? v[j + 1] + 1.f : fast_ex2(v[j + 1] * 1.4426950408889634f);
-                    v[j + 2] = v[j + 2] > 0.f ? v[j + 2] + 1.f : fast_ex2(v[j + 2] * 1.4426950408889634f);
-                    v[j + 3] = v[j + 3] > 0.f ? v[j + 3] + 1.f : fast_ex2(v[j + 3] * 1.4426950408889634f);
-                    dot = fmaf(v[j], k4.x, dot); dot = fmaf(v[j + 1], k4.y, dot); dot = fmaf(v[j + 2], k4.z, dot); dot = fmaf(v[j + 3], k4.w, dot);
+                for (int b = 0; b < 4; ++b) {
+                    float* v = va + 32 * b;
+                    const float* ks = p.ksum + seg * 256 + cb + 32 * b;
+                    float dot = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 k4 = __ldg(reinterpret_cast<const float4*>(ks + j));
+                        v[j] = v[j] > 0.f ? v[j] + 1.f : fast_ex2(v[j] * 1.4426950408889634f);          // elu(x) + 1
+                        v[j + 1] = v[j + 1] > 0.f ? v[j + 1] + 1.f : fast_ex2(v[j + 1] * 1.4426950408889634f);
+                        v[j + 2] = v[j + 2] > 0.f ? v[j + 2] + 1.f : fast_ex2(v[j + 2] * 1.4426950408889634f);
+                        v[j + 3] = v[j + 3] > 0.f ? v[j + 3] + 1.f : fast_ex2(v[j + 3] * 1.4426950408889634f);
+                        dot = fmaf(v[j], k4.x, dot); dot = fmaf(v[j + 1], k4.y, dot); dot = fmaf(v[j + 2], k4.z, dot); dot = fmaf(v[j + 3], k4.w, dot);
+                    }
+                    const float z = p.qz_scale[seg] / (dot + 1e-6f);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] *= z;
+                    uint32_t pk[32];
+                    pack_block_hl(v, pk);
+                    tmem_st32(tw + R0 + cb + 32 * b, pk);
                 }
-                const float z = p.qz_scale[seg] / (dot + 1e-6f);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] *= z;
-                uint32_t pk[32];
-                pack_block_hl(v, pk);
-                tmem_st32(tw + R0 + cb + 32 * b, pk);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -368,16 +393,20 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 mbar_wait(&h_done[j], tp);
                 tc_fence_after();
                 if (stamp && j == 0) enc_stamp(p, 9);
-#pragma unroll 1
-                for (int b = 0; b < 4; ++b) {
-                    float v[32];
-                    tmem_ld32(tw + R0 + cb + 32 * b, v);
+                {
+                    float va[128];
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) tmem_ld32(tw + R0 + cb + 32 * b, va + 32 * b);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-                    uint32_t pk[32];
-                    pack_block_hl(v, pk);
-                    tmem_st32(tw + R0 + cb + 32 * b, pk);
+                    for (int b = 0; b < 4; ++b) {
+                        float* v = va + 32 * b;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        uint32_t pk[32];
+                        pack_block_hl(v, pk);
+                        tmem_st32(tw + R0 + cb + 32 * b, pk);
+                    }
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -385,18 +414,72 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 if (lane == 0) mbar_arrive_remote(&hid_ready[j], 0);
                 if (stamp && j == 1) enc_stamp(p, 10);
             }
-            // ---- E4: x + LayerNorm2(acc_out) -> HBM (split planes [+ fp32]); the 32x32 store transposition is staged in act chunk 3
+            // ---- E4: x + LayerNorm2(acc_out) -> HBM
             mbar_wait(out_done, tp);
             tc_fence_after();
             if (stamp) enc_stamp(p, 12);
-            {
+            if (tma_e4) {
+                // residual tile (hi, lo) sits in act in the operand layout; normalise, add, split and write back in place, then one
+                // thread hands the 4 x 2 boxes to the TMA (no global load / store instruction in this epilogue)
+                float v[128];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tmem_ld32(tw + R1 + cb + 32 * b, v + 32 * b);
+                tmem_ld_wait();
+                const float pivot = v[0];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int j = 0; j < 128; ++j) { const float d = v[j] - pivot; s1 += d; s2 = fmaf(d, d, s2); }
+                const float m_own = pivot + s1 * (1.f / 128.f);
+                const float q_own = fmaxf(s2 - s1 * s1 * (1.f / 128.f), 0.f);
+                *reinterpret_cast<float2*>(lnx_own + 2 * lane) = make_float2(m_own, q_own);
+                named_bar_sync(1 + quad, 64);
+                const float2 o = *reinterpret_cast<const float2*>(lnx_partner + 2 * lane);
+                named_bar_sync(1 + quad, 64);
+                const float mean = 0.5f * (m_own + o.x);
+                const float dm = m_own - o.x;
+                const float var = (q_own + o.y + 64.f * dm * dm) * (1.f / 256.f);
+                const float scale = rsqrtf(var + 1e-5f), shift = -mean * scale;
+                mbar_wait(xr_full, tp);
+#pragma unroll
+                for (int j8 = 0; j8 < 16; ++j8) {
+                    const int col = cb + 8 * j8;
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.e4.gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(p.e4.gamma + col + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.e4.beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(p.e4.beta + col + 4));
+                    uint8_t* unit = act + (col >> 6) * kEncChunk + r * 128 + (((((col & 63) >> 3)) ^ (r & 7)) << 4);
+                    const uint4 rh = *reinterpret_cast<const uint4*>(unit), rl = *reinterpret_cast<const uint4*>(unit + 16384);
+                    const float* w = v + 8 * j8;
+                    float y0 = fmaf(fmaf(w[0], scale, shift), g0.x, b0.x), y1 = fmaf(fmaf(w[1], scale, shift), g0.y, b0.y);
+                    float y2 = fmaf(fmaf(w[2], scale, shift), g0.z, b0.z), y3 = fmaf(fmaf(w[3], scale, shift), g0.w, b0.w);
+                    float y4 = fmaf(fmaf(w[4], scale, shift), g1.x, b1.x), y5 = fmaf(fmaf(w[5], scale, shift), g1.y, b1.y);
+                    float y6 = fmaf(fmaf(w[6], scale, shift), g1.z, b1.z), y7 = fmaf(fmaf(w[7], scale, shift), g1.w, b1.w);
+                    add_f16x2(y0, y1, rl.x); add_f16x2(y2, y3, rl.y); add_f16x2(y4, y5, rl.z); add_f16x2(y6, y7, rl.w);   // same order as the
+                    add_f16x2(y0, y1, rh.x); add_f16x2(y2, y3, rh.y); add_f16x2(y4, y5, rh.z); add_f16x2(y6, y7, rh.w);   // register-path epilogue
+                    uint4 uh, ul;
+                    split_f16x2(y0, y1, uh.x, ul.x); split_f16x2(y2, y3, uh.y, ul.y);
+                    split_f16x2(y4, y5, uh.z, ul.z); split_f16x2(y6, y7, uh.w, ul.w);
+                    *reinterpret_cast<uint4*>(unit) = uh;
+                    *reinterpret_cast<uint4*>(unit + 16384) = ul;
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                named_bar_sync(6, 32 * 8);   // the eight epilogue warps of this CTA
+                if (warp == 2 && lane == 0) {
+                    const int m0 = (tile * 2 + static_cast<int>(rank)) * kBM;
+                    for (int c = 0; c < 4; ++c) {
+                        tma_store_3d(&maps.x, act + c * kEncChunk, c * 64, m0, 0);
+                        tma_store_3d(&maps.x, act + c * kEncChunk + 16384, c * 64, m0, 1);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read();   // act may be refilled (next tile's x) once the stores have read it
+                }
+            } else {
                 EpiCtx ctx;
                 ctx.stg = act + 3 * kEncChunk + (warp - 2) * 4096;
                 ctx.stg_partner = act + 3 * kEncChunk + ((warp - 2) ^ 4) * 4096;
                 ctx.bar_id = 1 + quad;
                 LinEpi::run_ln_staged<256, 2>(p.e4, tw + R1, row0, lane, 0, cb, ctx);
+                tc_fence_before();
             }
-            tc_fence_before();
             __syncwarp();
             if (lane == 0) { mbar_arrive_remote(e4_done, 0); mbar_arrive_remote(e4_done, 1); }
             if (stamp) enc_stamp(p, 13);
@@ -404,6 +487,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             tp ^= 1u;
         }
     }
+    if (warp == 2 && lane == 0) tma_store_wait_all();
     tc_fence_before();
     cluster_sync_all();
     if (threadIdx.x == 0) enc_stamp(p, 11);

@@ -960,15 +960,20 @@ struct KvEpi {
     static constexpr bool kHasState = true;
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = 4096;
+    // Register tile of a thread: 4 d x 4 v of each head's 32 x 32 outer-product sum (lane = (dq, vq): d = 4*dq + i, v = 16*half + 4*vq + j).
+    // Per staged row a thread then loads ONE 16-byte K unit and ONE 16-byte V unit for 16 FMAs -- a 128-bit shared load costs four
+    // wavefronts per warp whatever the addresses, so the (1 d x 16 v) tile of the first version (five loads per 16 FMAs, 17 wavefronts
+    // per row) made the epilogue LSU-bound at ~15 us per tile (profiles/r02_timeline_fused.log); this layout needs 8.
     struct State {
         float acc[4][16];
-        float ks[4];
+        float ks[4][4];
         int seg, nt;
     };
     static __device__ __forceinline__ void reset(State& st) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            st.ks[h] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) st.ks[h][j] = 0.f;
 #pragma unroll
             for (int j = 0; j < 16; ++j) st.acc[h][j] = 0.f;
         }
@@ -981,16 +986,20 @@ struct KvEpi {
     // combine the four quadrant pairs of this CTA in quadrant order and write the partial of (st.seg, st.nt)
     static __device__ __forceinline__ void flush(const Params& p, State& st, int lane, int half, int quad, uint8_t* epi_smem) {
         float* red = reinterpret_cast<float*>(epi_smem);  // 16.5 KB of the 32 KB staging area
+        const int dq = lane >> 2, vq = lane & 3;
         named_bar_sync(5, 32 * kGemm2EpiWarps);
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
             if (quad == q) {
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    float* r = red + (h * 32 + lane) * 33 + half * 16;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = (q == 0 ? 0.f : r[j]) + st.acc[h][j];
-                    if (half == 0) red[(h * 32 + lane) * 33 + 32] = (q == 0 ? 0.f : red[(h * 32 + lane) * 33 + 32]) + st.ks[h];
+                    for (int i = 0; i < 4; ++i) {
+                        float* r = red + (h * 32 + dq * 4 + i) * 33;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) r[half * 16 + vq * 4 + j] = (q == 0 ? 0.f : r[half * 16 + vq * 4 + j]) + st.acc[h][4 * i + j];
+                        if (half == 0 && vq == 0) r[32] = (q == 0 ? 0.f : r[32]) + st.ks[h][i];
+                    }
                 }
             }
             named_bar_sync(5, 32 * kGemm2EpiWarps);
@@ -1017,6 +1026,7 @@ struct KvEpi {
         const bool valid = row >= p.row_begin[seg] && row < p.row_end[seg];
         const uint8_t* kst = half == 0 ? ctx.stg : ctx.stg_partner;
         const uint8_t* vst = half == 0 ? ctx.stg_partner : ctx.stg;
+        const int dq = lane >> 2, vch = half * 4 + (lane & 3);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {  // unrolled: the per-head accumulators must stay in registers
             float v[32];
@@ -1030,26 +1040,22 @@ struct KvEpi {
             }
             LinEpi::stage_rows(ctx.stg, lane, v);
             named_bar_sync(ctx.bar_id, 64);
-            float ksum = 0.f;
-            float a[16];
+            float a[16], k0 = st.ks[h][0], k1 = st.ks[h][1], k2 = st.ks[h][2], k3 = st.ks[h][3];
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = st.acc[h][j];
-#pragma unroll 4
+#pragma unroll 8
             for (int r = 0; r < 32; ++r) {
-                const float k = *reinterpret_cast<const float*>(kst + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
-                ksum += k;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 w = LinEpi::unstage(vst, r, half * 4 + i);
-                    a[4 * i] = fmaf(k, w.x, a[4 * i]);
-                    a[4 * i + 1] = fmaf(k, w.y, a[4 * i + 1]);
-                    a[4 * i + 2] = fmaf(k, w.z, a[4 * i + 2]);
-                    a[4 * i + 3] = fmaf(k, w.w, a[4 * i + 3]);
-                }
+                const float4 k = LinEpi::unstage(kst, r, dq);
+                const float4 w = LinEpi::unstage(vst, r, vch);
+                k0 += k.x; k1 += k.y; k2 += k.z; k3 += k.w;
+                a[0] = fmaf(k.x, w.x, a[0]);   a[1] = fmaf(k.x, w.y, a[1]);   a[2] = fmaf(k.x, w.z, a[2]);   a[3] = fmaf(k.x, w.w, a[3]);
+                a[4] = fmaf(k.y, w.x, a[4]);   a[5] = fmaf(k.y, w.y, a[5]);   a[6] = fmaf(k.y, w.z, a[6]);   a[7] = fmaf(k.y, w.w, a[7]);
+                a[8] = fmaf(k.z, w.x, a[8]);   a[9] = fmaf(k.z, w.y, a[9]);   a[10] = fmaf(k.z, w.z, a[10]); a[11] = fmaf(k.z, w.w, a[11]);
+                a[12] = fmaf(k.w, w.x, a[12]); a[13] = fmaf(k.w, w.y, a[13]); a[14] = fmaf(k.w, w.z, a[14]); a[15] = fmaf(k.w, w.w, a[15]);
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) st.acc[h][j] = a[j];
-            st.ks[h] += ksum;
+            st.ks[h][0] = k0; st.ks[h][1] = k1; st.ks[h][2] = k2; st.ks[h][3] = k3;
             named_bar_sync(ctx.bar_id, 64);  // both warps are done reading the staged blocks
         }
     }
