@@ -448,7 +448,7 @@ def main():
         for _ in range(steps):
             out = fn()
             if gather and world > 1:
-                D.gather_varlen([o if torch.is_tensor(o) else torch.from_numpy(o).to(dev) for o in out])
+                D.gather_varlen_to([o if torch.is_tensor(o) else torch.from_numpy(o).to(dev) for o in out], dst=0)   # only rank 0 receives
         e1.record()
         torch.cuda.synchronize()
         D.barrier()
@@ -560,8 +560,9 @@ def main():
                "ms_per_chunk": ms2 / k2, "tracks_per_chunk": args.hp2_tracks, "patches_per_chunk": n_patches,
                "e2e": {"value": args.hp2_tracks * k2 * world / (ms2_e2e * 1e-3), "unit": "tracks/s",
                        "h2d_bytes_per_step": h2d_2, "d2h_bytes_per_step": d2h_2,
-                       "note": "host chunk dict (pinned) -> device, matcher call, refined points + std -> host; copies the host shim makes "
-                               "internally (index arrays staged for the C ABI) are inside the timed region but not in these byte counts"},
+                       "note": "host chunk dict (pinned) -> device, matcher call, refined points + std -> host; inside the call the shim reads the "
+                               "small per-track arrays back ONCE as one packed buffer (the C ABI builds its patch records on the host; ~0.5 MB, "
+                               "not in these counts) and leaves the results on the device"},
                "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,split,ConvEpi> (S2DNet patch convolutions, persistent CTA pairs)",
                             "achieved": pconv_alg / (pc_ms * 1e-3) / 1e12 if pc_ms else None, "peak": peaks["tflops"], "unit": "TFLOP/s",
                             "frac": pconv_alg / (pc_ms * 1e-3) / 1e12 / peaks["tflops"] if pc_ms else None,
