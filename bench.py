@@ -320,7 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "1")),
+    ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "2")),
                     help="concurrent pair workers per GPU, each with its own matcher (engine handle + workspaces) and CUDA stream -- the reference "
                          "deploys two Ray workers per GPU (n_gpus_per_worker: 0.5, src/coarse_match/coarse_match.py:53)")
     ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
@@ -418,24 +418,43 @@ def main():
 
     h2d = d2h = 0
 
+    def run_pairs_e2e(widx, todo, cached, res, dev_out, counts):
+        """one pair worker of the end-to-end leg: the plugin call from HOST buffers -- pinned images -> device, matcher(data), the
+        (M,5) match array back to the host -- on the worker's own stream"""
+        mw, stream = workers[widx]
+        torch.cuda.set_device(local)
+        up = down = 0
+        with torch.cuda.stream(stream):
+            for k in todo:
+                i, j = pairs[k]
+                a, b = host_images[i].to(dev, non_blocking=True), host_images[j].to(dev, non_blocking=True)
+                up += a.numel() * 4 + b.numel() * 4
+                data = {"image0": a, "image1": b, "scale0": ones, "scale1": ones}
+                if cached:
+                    data["pair_key"] = ((f"im{i}",), (f"im{j}",))
+                mw(data)
+                md = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
+                dev_out[k] = md
+                m = md.cpu().numpy()
+                down += m.nbytes + 4  # + the match-count readback that sizes the arrays
+                res[k] = m
+        counts[widx] = (up, down)
+
     def step_e2e(cached):
-        """the plugin call from HOST buffers: pinned images -> device each pair, (M,5) match arrays back to the host"""
+        """the plugin call from HOST buffers for every pair (+ the merge of the step's matches, results to the host)"""
         nonlocal h2d, d2h
-        matcher._cache.clear()
-        h2d = d2h = 0
-        res, dev_out = [], []
-        for (i, j) in pairs:
-            a, b = host_images[i].to(dev, non_blocking=True), host_images[j].to(dev, non_blocking=True)
-            h2d += a.numel() * 4 + b.numel() * 4
-            data = {"image0": a, "image1": b, "scale0": ones, "scale1": ones}
-            if cached:
-                data["pair_key"] = ((f"im{i}",), (f"im{j}",))
-            matcher(data)
-            md = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
-            dev_out.append(md)
-            m = md.cpu().numpy()
-            d2h += m.nbytes + 4  # + the match-count readback that sizes the arrays
-            res.append(m)
+        for mw, _ in workers:
+            mw._cache.clear()
+        res, dev_out, counts = [None] * len(pairs), [None] * len(pairs), [None] * n_workers
+        ths = [threading.Thread(target=run_pairs_e2e, args=(w, range(w, len(pairs), n_workers), cached, res, dev_out, counts))
+               for w in range(1, n_workers)]
+        for t in ths:
+            t.start()
+        run_pairs_e2e(0, range(0, len(pairs), n_workers), cached, res, dev_out, counts)
+        for t in ths:
+            t.join()                                  # every worker has read its last match array back: its stream is drained
+        h2d = sum(c[0] for c in counts)
+        d2h = sum(c[1] for c in counts)
         kp = [t.cpu() for t in merge_step(dev_out)]   # keypoints, scores, per-image offsets, per-match keypoint ids -> host
         d2h += sum(t.numel() * t.element_size() for t in kp)
         return res
@@ -464,6 +483,12 @@ def main():
     ms_cold = timed(lambda: step_resident(False), K, True)
     launches = lib.dfsfm_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    ms_cold_1w = None
+    if n_workers > 1:     # the same step with ONE pair in flight (per-pair latency view; explains what the pair workers buy)
+        saved_w, n_workers = n_workers, 1
+        step_resident(False)
+        ms_cold_1w = timed(lambda: step_resident(False), K, False)
+        n_workers = saved_w
     step_resident(True)   # every variant gets its own untimed warm-up step (allocator growth, feature-cache storage)
     ms_cached = timed(lambda: step_resident(True), K, True)
     step_e2e(False)
@@ -709,6 +734,7 @@ def main():
                        "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays",
                        "pair_workers_per_gpu": n_workers},
             "value_cached": n_pairs * K / (ms_cached * 1e-3),
+            "value_one_pair_in_flight": (n_pairs * K / (ms_cold_1w * 1e-3)) if ms_cold_1w else None,
             "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "value_cached": n_pairs * K / (ms_e2e_cached * 1e-3)},
             "matches_per_pair": {"mean": float(np.mean(m_stats["counts"])), "min": int(min(m_stats["counts"])), "max": int(max(m_stats["counts"])),
