@@ -143,8 +143,10 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) enc_stamp(p, 1);
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == 0) enc_stamp(p, 2);
+    // Programmatic dependent launch: everything that reads what the previous kernels wrote (x, G, Ksum) waits here -- except the TMA
+    // producer, which first puts the first weight chunks (they depend on nothing) in flight and waits just before its first x load.
+    if (warp != 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (threadIdx.x == 32) enc_stamp(p, 2);
     constexpr uint32_t R0 = 0, R1 = 256;
     const bool tma_e4 = p.e4.out_f32 == nullptr;   // the last layer also writes an fp32 copy: it keeps the register-path epilogue
 
@@ -163,6 +165,8 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 tma_load_3d_2sm(st + 16384, m, &r_full[s], col, row, 1);
                 ++it;
             };
+            for (int c = 0; c < 3; ++c) ring_load(&maps.wq, c * 64, static_cast<int>(rank) * 128);   // ahead of the dependency wait
+            asm volatile("griddepcontrol.wait;" ::: "memory");
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int m0 = (tile * 2 + static_cast<int>(rank)) * kBM;
                 const int seg = (p.seg_tile0 > 0 && tile >= p.seg_tile0) ? 1 : 0;
@@ -174,7 +178,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     if (rank == 0) mbar_arrive_expect_tx(&x_full[c], 2 * kEncChunk);
                     tma_load_3d_2sm(act + c * kEncChunk, &maps.x, &x_full[c], c * 64, m0, 0);
                     tma_load_3d_2sm(act + c * kEncChunk + 16384, &maps.x, &x_full[c], c * 64, m0, 1);
-                    ring_load(&maps.wq, c * 64, wrow);
+                    if (!(first && c < 3)) ring_load(&maps.wq, c * 64, wrow);
                 }
                 for (int c = 0; c < 4; ++c) ring_load(&maps.g, c * 64, seg * 256 + wrow);
                 for (int j = 0; j < 2; ++j) {
