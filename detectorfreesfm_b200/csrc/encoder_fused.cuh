@@ -116,7 +116,8 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     uint64_t* hid_ready = bars + 19;    // [2]
     uint64_t* e4_done = bars + 21;      // epilogue warps of both CTAs -> BOTH CTAs (16 arrivals each)
     uint64_t* xr_full = bars + 22;      // residual x tile landed in act (per CTA, local TMA)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+    uint64_t* x0_done = bars + 23;      // MMA commit: the x part of mlp.0 chunk 0 has read x from act (the epilogue may overwrite it with m)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     float* lnx = reinterpret_cast<float*>(smem + kEncLnxOff);
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -135,6 +136,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
         mbar_init(qp_ready, 16); mbar_init(m_ready, 16); mbar_init(&hid_ready[0], 16); mbar_init(&hid_ready[1], 16);
         mbar_init(e4_done, 16);
         mbar_init(xr_full, 1);
+        mbar_init(x0_done, 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm<512>(tmem_slot);
@@ -183,7 +185,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 for (int c = 0; c < 4; ++c) ring_load(&maps.g, c * 64, seg * 256 + wrow);
                 for (int j = 0; j < 2; ++j) {
                     for (int c = 0; c < 4; ++c) {
-                        ring_load(&maps.x, c * 64, m0);
+                        if (j == 1) ring_load(&maps.x, c * 64, m0);   // chunk 0's x part runs while x is still resident in act
                         ring_load(&maps.w0, c * 64, j * 256 + wrow);
                     }
                     for (int c = 0; c < 4; ++c) ring_load(&maps.w0, 256 + c * 64, j * 256 + wrow);
@@ -261,17 +263,30 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     ring_release(b);
                 }
                 umma_commit_2sm(mg_done);
+                // ---- mlp.0, x part of hidden chunk 0, while x is still resident in act: it runs under the LayerNorm1 epilogue, which
+                //      waits for x0_done before it overwrites act with m.  R0 is the A operand of GEMM2 until that has completed.
+                mbar_wait(mg_done, tp);
+                tc_fence_after();
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t b = ring_wait();
+                    mma_ss(R0, act_a + c * kEncChunk, b, c == 0);
+                    ring_release(b);
+                }
+                umma_commit_2sm(x0_done);
                 // ---- mlp: two 256-wide chunks of the hidden layer
                 mbar_wait(m_ready, tp);
                 tc_fence_after();
                 for (int j = 0; j < 2; ++j) {
-                    if (j == 1) { mbar_wait(g4_done, tp); tc_fence_after(); }   // relu(hid chunk 0) in R0 is no longer being read
-                    for (int c = 0; c < 4; ++c) {                                // x part of mlp.0 (x re-streamed through the ring)
-                        const uint32_t a = ring_wait();
-                        const uint32_t b = ring_wait();
-                        mma_ss(R0, a, b, c == 0);
-                        ring_release(a);
-                        ring_release(b);
+                    if (j == 1) {
+                        mbar_wait(g4_done, tp);                                  // relu(hid chunk 0) in R0 is no longer being read
+                        tc_fence_after();
+                        for (int c = 0; c < 4; ++c) {                            // x part of chunk 1 (x re-streamed through the ring)
+                            const uint32_t a = ring_wait();
+                            const uint32_t b = ring_wait();
+                            mma_ss(R0, a, b, c == 0);
+                            ring_release(a);
+                            ring_release(b);
+                        }
                     }
                     for (int c = 0; c < 4; ++c) {                                // m part (m resident in act)
                         const uint32_t b = ring_wait();
@@ -367,6 +382,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 const float dm = m_own - o.x;
                 const float var = (q_own + o.y + 64.f * dm * dm) * (1.f / 256.f);   // Chan: n_a n_b / n * dm^2 = 64 dm^2
                 const float scale = rsqrtf(var + 1e-5f), shift = -mean * scale;
+                mbar_wait(x0_done, tp);   // the tensor core has finished reading x from act (x part of mlp.0 chunk 0)
 #pragma unroll
                 for (int j8 = 0; j8 < 16; ++j8) {   // 8 columns = one 16-byte unit of the operand row
                     const int col = cb + 8 * j8;
