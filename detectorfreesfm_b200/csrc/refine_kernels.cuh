@@ -55,21 +55,36 @@ static __global__ void __launch_bounds__(256) patch_conv11_kernel(const PatchRec
     for (int i = 0; i < 27; ++i) wr[i] = w[c * 27 + i];
     const float b = bias[c];
     const long long base = static_cast<long long>(blockIdx.x) * kCropP * kCropP;
-    for (int pix = phase; pix < kCrop * kCrop; pix += 4) {
-        const int y = pix / kCrop, x = pix - y * kCrop;
-        float acc = 0.f;
+    // four adjacent output pixels per pass: a 3 x 6 input window per colour feeds 4 x 27 FMAs (18 shared loads instead of 4 x 27 --
+    // the one-pixel version was bound by the shared-memory pipe, one broadcast load per FMA)
+    constexpr int kGroups = (kCrop + 3) / 4;
+    for (int g = phase; g < kCrop * kGroups; g += 4) {
+        const int y = g / kGroups, x0 = (g - y * kGroups) * 4;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int d = 0; d < 3; ++d)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+            for (int ky = 0; ky < 3; ++ky) {
+                float in[6];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) acc = fmaf(wr[d * 9 + ky * 3 + kx], tile[d][y + ky][x + kx], acc);
-        acc = fmaxf(acc + b, 0.f);
-        __half h, l;
-        split_f16(acc, h, l);
-        const long long o = (base + y * kCropP + x) * 64 + c;
-        out_hi[o] = h;
-        out_lo[o] = l;
+                for (int i = 0; i < 6; ++i) in[i] = tile[d][y + ky][x0 + i];
+#pragma unroll
+                for (int px = 0; px < 4; ++px)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) acc[px] = fmaf(wr[d * 9 + ky * 3 + kx], in[px + kx], acc[px]);
+            }
+#pragma unroll
+        for (int px = 0; px < 4; ++px) {
+            const int x = x0 + px;
+            if (x < kCrop) {
+                const float a = fmaxf(acc[px] + b, 0.f);
+                __half h, l;
+                split_f16(a, h, l);
+                const long long o = (base + y * kCropP + x) * 64 + c;
+                out_hi[o] = h;
+                out_lo[o] = l;
+            }
+        }
     }
 }
 
