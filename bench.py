@@ -394,7 +394,7 @@ def main():
         nonlocal n_workers
         out = [None] * len(pairs)
         for mw, _ in workers:
-            mw._cache.clear()
+            mw.clear_cache()
         if n_workers == 1:
             run_pairs(0, range(len(pairs)), cached, out)
         else:
@@ -444,7 +444,7 @@ def main():
         """the plugin call from HOST buffers for every pair (+ the merge of the step's matches, results to the host)"""
         nonlocal h2d, d2h
         for mw, _ in workers:
-            mw._cache.clear()
+            mw.clear_cache()
         res, dev_out, counts = [None] * len(pairs), [None] * len(pairs), [None] * n_workers
         ths = [threading.Thread(target=run_pairs_e2e, args=(w, range(w, len(pairs), n_workers), cached, res, dev_out, counts))
                for w in range(1, n_workers)]

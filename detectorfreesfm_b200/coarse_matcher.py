@@ -16,7 +16,7 @@ from .packing import pack_loftr, position_encoding
 
 
 class B200LoFTR(torch.nn.Module):
-    def __init__(self, config, device=None, feature_cache_size=64):
+    def __init__(self, config, device=None, feature_cache_size=64, feature_cache_bytes=8 << 30):
         super().__init__()
         self.config = config
         mc = config["match_coarse"]
@@ -40,8 +40,13 @@ class B200LoFTR(torch.nn.Module):
         self._h = ctypes.c_void_p()
         self._device = None
         self._pe = {}
+        # per-image feature cache (exact: BatchNorm is in eval mode).  Key contract: (pair_key name, H, W) -- the caller guarantees that a
+        # name keeps its pixels for the life of the cache (one scene); call clear_cache() between scenes that reuse relative paths.
+        # Bounded by entries AND bytes (with the fine stage an entry holds the 1/2-resolution 128-channel map: 140-270 MB at 1200-1600 px).
         self._cache = OrderedDict()
         self._cache_size = feature_cache_size
+        self._cache_bytes_max = int(feature_cache_bytes)
+        self._cache_bytes = 0
         self._packed = None
         if device is not None:
             self.cuda(device)
@@ -69,7 +74,7 @@ class B200LoFTR(torch.nn.Module):
         self._packed = pack_loftr(state_dict, fine=self.fine)
         if self._h:
             self._upload()
-        self._cache.clear()
+        self.clear_cache()
         return self
 
     def _upload(self):
@@ -82,6 +87,7 @@ class B200LoFTR(torch.nn.Module):
             self._h = ctypes.c_void_p()
         self._pe.clear()
         self._cache.clear()
+        self._cache_bytes = 0
 
     def __del__(self):
         try:
@@ -117,9 +123,12 @@ class B200LoFTR(torch.nn.Module):
                                                        _lib.stream_ptr(self._device)))
             out = tokens
         if key is not None:
+            nbytes = sum(t.numel() * t.element_size() for t in (out if isinstance(out, tuple) else (out,)))
             self._cache[key] = out
-            while len(self._cache) > self._cache_size:
-                self._cache.popitem(last=False)
+            self._cache_bytes += nbytes
+            while len(self._cache) > 1 and (len(self._cache) > self._cache_size or self._cache_bytes > self._cache_bytes_max):
+                _, old = self._cache.popitem(last=False)
+                self._cache_bytes -= sum(t.numel() * t.element_size() for t in (old if isinstance(old, tuple) else (old,)))
         return out
 
     def fine_match(self, feat_f0, hw0_f, feat_f1, hw1_f, feat_c0, hw0_c, feat_c1, hw1_c, i_ids, j_ids):
@@ -167,6 +176,7 @@ class B200LoFTR(torch.nn.Module):
         """Drop the per-image feature cache.  Entries are keyed by (pair_key name, H, W): a caller that re-uses a name for
         different pixels (another dataset root with the same relative paths) must clear it between scenes."""
         self._cache.clear()
+        self._cache_bytes = 0
 
     def _forward(self, data):
         if not self._h:
