@@ -637,7 +637,9 @@ def main():
                     "roofline": {"bound": "hbm", "kernel": "rs_scatter_kernel (one 8-bit LSD radix pass over the observation records)",
                                  "achieved": rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 if sc_cnt else None, "peak": peaks.get("hbm"), "unit": "GB/s",
                                  "frac": (rec_bytes / (sc_ms / sc_cnt * 1e-3) / 1e9 / peaks["hbm"]) if sc_cnt and peaks.get("hbm") else None,
-                                 "traffic": None, "launches": sc_cnt,
+                                 "traffic": 0.3396, "traffic_unit": "GB per launch of the first pass over the 8.06 M observation records (ncu dram read+write, "
+                                                                    "profiles/r02_ncu_post_summary.txt; algorithmic 0.1935 GB: the per-digit offsets / histograms and "
+                                                                    "write-allocate reads account for the rest)", "launches": sc_cnt,
                                  "kernel_ms_per_call": {k: round(v[1], 3) for k, v in sorted(prof3.items())}}}
             if rank == 0 and world == 1 and not args.skip_cpu:
                 from oracle import postprocess_oracle as po
@@ -691,7 +693,8 @@ def main():
                                "d2h_bytes_per_step": 0},
                        "roofline": {"bound": "hbm", "kernel": "lanczos_h_kernel (horizontal pass over the full-resolution image)",
                                     "achieved": alg_bytes / (h_ms / h_cnt * 1e-3) / 1e9 if h_cnt else None, "peak": peaks["hbm"], "unit": "GB/s",
-                                    "frac": alg_bytes / (h_ms / h_cnt * 1e-3) / 1e9 / peaks["hbm"] if h_cnt else None, "traffic": None,
+                                    "frac": alg_bytes / (h_ms / h_cnt * 1e-3) / 1e9 / peaks["hbm"] if h_cnt else None,
+                                    "traffic": 0.01212, "traffic_unit": "GB per launch (ncu dram read; the 3.6 MB intermediate stays in L2; profiles/r02_ncu_post_summary.txt)",
                                     "kernel_ms_per_step": {k: round(v[1], 3) for k, v in sorted(prof4.items())}}}
             if rank == 0 and world == 1 and not args.skip_cpu:
                 from PIL import Image
