@@ -86,3 +86,32 @@ def match_worker(chunks, matcher, colmap_image_ids, device=None, freeze=False):
         pt_idxs = np.concatenate([q_idx, r_idx], axis=0)
         results.append(np.concatenate([pts, img_ids[:, None], pt_idxs[:, None]], axis=1))   # M * 4
     return results
+
+
+def update_refined_kpts_to_colmap_multiview(colmap_images, fine_match_results):
+    """``CoarseColmapDataset.update_refined_kpts_to_colmap_multiview`` (src/dataset/coarse_sfm_refinement_dataset.py:333-341): write the
+    refined key points of ``match_worker``'s ``[K,4]`` arrays (x, y, image id, point2D index) back into ``colmap_images[id].xys`` (+0.5 px),
+    to every key point of the image that observes the same 3-D point (``point3D_ids`` duplicates).  The reference walks the results one by
+    one with an ``np.where`` over the image's key points each (quadratic); here the rows are grouped by image and applied with one
+    vectorised assignment per image, keeping the reference's order semantics: a later row for the same 3-D point overwrites an earlier one."""
+    rows = [np.asarray(r, dtype=np.float64).reshape(-1, 4) for r in fine_match_results]
+    if not rows:
+        return
+    rows = np.concatenate(rows, 0)
+    if rows.shape[0] == 0:
+        return
+    img = rows[:, 2].astype(np.int64)
+    order = np.argsort(img, kind="stable")                       # per image, rows stay in result order
+    img_sorted = img[order]
+    starts = np.flatnonzero(np.r_[True, img_sorted[1:] != img_sorted[:-1]])
+    ends = np.r_[starts[1:], len(order)]
+    for a, b in zip(starts.tolist(), ends.tolist()):
+        image = colmap_images[int(img_sorted[a])]
+        sel = order[a:b]
+        p3d = image.point3D_ids[rows[sel, 3].astype(np.int64)]
+        uniq, first_rev = np.unique(p3d[::-1], return_index=True)      # last occurrence of every 3-D point id wins
+        last = len(p3d) - 1 - first_rev
+        k = np.searchsorted(uniq, image.point3D_ids)
+        k = np.minimum(k, len(uniq) - 1)
+        hit = uniq[k] == image.point3D_ids
+        image.xys[hit] = rows[sel[last[k[hit]]], :2] + 0.5

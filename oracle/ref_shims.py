@@ -430,3 +430,20 @@ def import_chunk_dataset():
     dc.__path__ = [os.path.join(REF, "src", "post_optimization", "data_construct")]
     mod = importlib.import_module("src.post_optimization.data_construct.construct_matching_data")
     return mod.MatchingMultiviewData
+
+
+def import_colmap_dataset_class():
+    """-> the reference's ``CoarseColmapDataset`` class (src/dataset/coarse_sfm_refinement_dataset.py) for calling single methods unbound
+    on a stand-in ``self`` (update_refined_kpts_to_colmap_multiview); h5py / albumentations / ray are inert."""
+    _install_stubs()
+    for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        del sys.modules[k]
+    src = _mod("src")
+    src.__path__ = [os.path.join(REF, "src")]
+    for name in ("h5py", "albumentations"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            _mod(name)
+    _stub_ray()
+    return importlib.import_module("src.dataset.coarse_sfm_refinement_dataset").CoarseColmapDataset

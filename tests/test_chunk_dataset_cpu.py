@@ -92,3 +92,42 @@ def test_chunk_dataset_vs_golden():
         got = ours[i]
         assert len(got.pop("images")) == len(g["bags"][i]["bag_image_ids"])
         _compare_items(got, item)
+
+
+def _writeback_case(seed):
+    import copy
+    import types
+    rng = np.random.default_rng(seed)
+    ims = {}
+    for cid in (3, 7, 11):
+        n = 40
+        ims[cid] = types.SimpleNamespace(point3D_ids=rng.integers(-1, 12, n).astype(np.int64), xys=rng.normal(0, 100, (n, 2)))
+    results = [np.stack([np.r_[rng.normal(0, 50, 2), cid, rng.integers(0, 40)] for cid in rng.choice([3, 7, 11], 30)]) for _ in range(4)]
+    return ims, copy.deepcopy(ims), results
+
+
+def test_colmap_writeback_matches_the_reference_loop():
+    """refine_stage.update_refined_kpts_to_colmap_multiview (vectorised, grouped by image) vs the reference's row-by-row loop
+    (coarse_sfm_refinement_dataset.py:333-341, restated here): duplicates of a 3-D point in an image all move, later rows win."""
+    from detectorfreesfm_b200 import refine_stage as rs
+    for seed in range(3):
+        a, b, results = _writeback_case(seed)
+        for bag in results:                                    # the reference loop
+            for row in bag:
+                loc, image_id, idx = row[:2], int(row[2]), int(row[3])
+                pid = a[image_id].point3D_ids[idx]
+                dup = np.concatenate(np.where(a[image_id].point3D_ids == pid), axis=0)
+                a[image_id].xys[dup, :] = loc + 0.5
+        rs.update_refined_kpts_to_colmap_multiview(b, results)
+        assert all(np.array_equal(a[c].xys, b[c].xys) for c in a)
+
+
+@pytest.mark.skipif(not ref_shims.available(), reason="/root/reference not present")
+def test_colmap_writeback_matches_the_reference_method():
+    import types
+    from detectorfreesfm_b200 import refine_stage as rs
+    Ref = ref_shims.import_colmap_dataset_class()
+    a, b, results = _writeback_case(5)
+    Ref.update_refined_kpts_to_colmap_multiview(types.SimpleNamespace(colmap_images=a), results)
+    rs.update_refined_kpts_to_colmap_multiview(b, results)
+    assert all(np.array_equal(a[c].xys, b[c].xys) for c in a)
