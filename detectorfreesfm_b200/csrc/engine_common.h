@@ -87,7 +87,7 @@ inline bool fused_mlp_enabled() {
 inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long long T, const HL& w0, const HL& w2, const float* gamma,
                                 const float* beta, float* xf, cudaStream_t st) {
     static PerDeviceOnce once;
-    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(mlp128_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemBytes));
+    once.run([&] { DFSFM_CUDA(cudaFuncSetAttribute(mlp128_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMlpSmemBytes)); });
     MlpMaps maps;
     maps.x = make_tmap(x.hi + row0 * 128, 128, T, x.plane_elems(), 128);
     maps.m1 = make_tmap(m1.hi + row0 * 128, 128, T, m1.plane_elems(), 128);
@@ -122,7 +122,7 @@ inline void launch_mlp128_fused(const HL& x, const HL& m1, long long row0, long 
 inline void launch_enc256_fused(const HL& x, long long row0, long long T, const HL& wqkv, const HL& g, const HL& w0, const HL& w2, EncParams p,
                                 cudaStream_t st) {
     static PerDeviceOnce once;
-    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(enc256_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes));
+    once.run([&] { DFSFM_CUDA(cudaFuncSetAttribute(enc256_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kEncSmemBytes)); });
     EncMaps maps;
     maps.x = make_tmap(x.hi + row0 * 256, 256, T, x.plane_elems(), 128);
     maps.wq = make_tmap(wqkv.hi, 256, 256, wqkv.plane_elems(), 128);

@@ -6,7 +6,9 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -97,12 +99,18 @@ inline int current_device() {
     return dev;
 }
 struct PerDeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
-    bool first() {  // true exactly once per device
+    // runs f exactly once per device; other host threads launching the same kernel for the first time wait until it has finished (one
+    // engine handle per thread may drive the GPU concurrently: a launch must not overtake the cudaFuncSetAttribute of its own kernel)
+    template <class F>
+    void run(F&& f) {
         const int d = current_device() & 63;
-        if (done[d]) return false;
-        done[d] = true;
-        return true;
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[d]) {
+            f();
+            done[d] = true;
+        }
     }
 };
 
@@ -111,17 +119,21 @@ inline void launch_gemm(const TmapPack& maps, const GemmCore& core, const typena
     using Cfg = GemmCfg<BN, kSplit>;
     auto kern = gemm_tc_kernel<BN, kSplit, Epi>;
     static PerDeviceOnce once;
-    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    once.run([&] { DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); });
     dim3 grid((core.M + kBM - 1) / kBM, (n_total + BN - 1) / BN);
     kern<<<grid, kGemmThreads, Cfg::kSmemBytes, st>>>(maps, core, ep);
     DFSFM_CUDA(cudaGetLastError());
 }
 
 inline int sm_count() {
-    static int n[64] = {};
+    static std::atomic<int> n[64];
     const int dev = current_device();
-    if (!n[dev & 63]) DFSFM_CUDA(cudaDeviceGetAttribute(&n[dev & 63], cudaDevAttrMultiProcessorCount, dev));
-    return n[dev & 63];
+    int v = n[dev & 63].load(std::memory_order_relaxed);
+    if (!v) {
+        DFSFM_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev));
+        n[dev & 63].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 inline bool pdl_enabled() {
     static int v = -1;
@@ -158,7 +170,7 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
                         "taps of a group must read the same map at consecutive row shifts");
     }
     static PerDeviceOnce once;
-    if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    once.run([&] { DFSFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes)); });
     const int m_pairs = (core.M + 2 * kBM - 1) / (2 * kBM);
     const int n_tiles = (n_total + BN - 1) / BN;
     const int tiles = m_pairs * n_tiles;

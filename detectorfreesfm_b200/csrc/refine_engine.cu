@@ -377,7 +377,7 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
         const int L = LW_ * LW_;
         const size_t smem = fine_match_smem_bytes(W_, LW_);
         static PerDeviceOnce once;
-        if (once.first()) DFSFM_CUDA(cudaFuncSetAttribute(fine_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        once.run([&] { DFSFM_CUDA(cudaFuncSetAttribute(fine_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); });
         { LaunchScope ls("finematch", st);
           fine_match_kernel<<<M, kFmThreads, smem, st>>>(xf_.p, d_tracks_.p, d_views_.p, Nq, W_, LW_, d_query_.p, d_ref_.p, d_std_.p, M); }
         DFSFM_CUDA(cudaGetLastError());
