@@ -61,3 +61,13 @@ def run():
     out_img = GpuImageReader().resize_gray(photo, (160, 120)).cpu().numpy()
     assert np.array_equal(out_img, ref_img)
     print("[smoke] image pipeline: 300x400 -> 120x160 PIL-LANCZOS parity, bit-exact")
+
+    # chunk dataset: native bag assignment + chunk dicts feeding the refinement matcher
+    from detectorfreesfm_b200 import B200MatchingMultiviewData
+    from detectorfreesfm_b200 import refine_stage as rs
+    ds = util.SynthColmapDataset(n_images=10, n_points=60, max_obs=6, seed=3, hw=(96, 128), dup_frac=0.0)
+    chunks = B200MatchingMultiviewData(ds, {"max_track_length": 16, "chunk": 40})
+    res = rs.match_worker(torch.utils.data.DataLoader(chunks, num_workers=0), rm, list(ds.colmap_images.keys()))
+    nodes = sum(r.shape[0] for r in res)
+    assert nodes >= sum(len(set(p.image_ids.tolist())) for p in ds.colmap_3ds.values()) and all(np.isfinite(r).all() for r in res)
+    print(f"[smoke] chunk dataset -> refinement worker loop: {len(chunks)} chunks, {nodes} refined nodes")
