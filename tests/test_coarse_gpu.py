@@ -145,3 +145,18 @@ def test_unequal_image_sizes_and_empty_match_set(sd):
             assert data["mkpts0_f"].shape == (0, 2) and data["m_bids"].shape == (0,)
         else:
             assert torch.equal(data["mkpts1_f"].cpu(), ref["mkpts1_f"])
+
+
+@pytest.mark.parametrize("env", [{"DFSFM_ATTN_FOLD": "0"}, {"DFSFM_KV_EPI": "0"}, {"DFSFM_ENC_FUSED": "0"}, {}])
+def test_transformer_schedules_agree_with_oracle(env):
+    """The A/B schedules of the coarse transformer (round-1 GEMM-per-linear + attn_apply; folded attention with the fp32-state
+    reduction; folded + KvEpi with four GEMM launches; the fused kernel) all meet the same parity bar.  The switches are read once per
+    process, hence a subprocess per schedule (tests/check_transformer.py)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "check_transformer.py")], env=e, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
