@@ -235,34 +235,22 @@ static __global__ void __launch_bounds__(kFmThreads) fine_match_kernel(const flo
         __syncthreads();
         for (int l0 = warp * kFmLB; l0 < L; l0 += (kFmThreads / 32) * kFmLB) {
             float sim[kFmLB][8];  // W*W <= 225 -> at most 8 window cells per lane
-            // channel loop outermost: one float4 of candidate features and the lane's (up to) 8 window-cell values feed 32 FMAs (the
-            // cell-outer order re-read the candidate features 8 times: 1.25 shared-memory wavefronts per FMA instead of 0.4)
 #pragma unroll
-            for (int li = 0; li < kFmLB; ++li)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) sim[li][k] = 0.f;
-            {
-                const float* rf = refT + l0;
-                int roff[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) roff[k] = min(lane + 32 * k, WW - 1) * (C + 1);   // out-of-window cells read a valid row, masked below
-                const int kmax = (WW + 31) / 32;   // warp-uniform: 8 for W = 15, 4 for W = 11, 2 for W = 7, 1 for the 5x5 windows of loftr_fine
-#pragma unroll 4
-                for (int c = 0; c < C; ++c) {
-                    const float4 rv = *reinterpret_cast<const float4*>(rf + c * Lp);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        if (k >= kmax) break;
-                        const float qv = qry[roff[k] + c];
-                        sim[0][k] = fmaf(rv.x, qv, sim[0][k]); sim[1][k] = fmaf(rv.y, qv, sim[1][k]);
-                        sim[2][k] = fmaf(rv.z, qv, sim[2][k]); sim[3][k] = fmaf(rv.w, qv, sim[3][k]);
+            for (int k = 0; k < 8; ++k) {
+                const int r = lane + 32 * k;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                if (r < WW) {
+                    const float* qr = qry + r * (C + 1);
+                    const float* rf = refT + l0;
+#pragma unroll 8
+                    for (int c = 0; c < C; ++c) {
+                        const float qv = qr[c];
+                        const float4 rv = *reinterpret_cast<const float4*>(rf + c * Lp);
+                        a0 = fmaf(rv.x, qv, a0); a1 = fmaf(rv.y, qv, a1); a2 = fmaf(rv.z, qv, a2); a3 = fmaf(rv.w, qv, a3);
                     }
                 }
+                sim[0][k] = a0 * inv_sqrt_c; sim[1][k] = a1 * inv_sqrt_c; sim[2][k] = a2 * inv_sqrt_c; sim[3][k] = a3 * inv_sqrt_c;
             }
-#pragma unroll
-            for (int li = 0; li < kFmLB; ++li)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) sim[li][k] = (lane + 32 * k < WW) ? sim[li][k] * inv_sqrt_c : 0.f;
 #pragma unroll
             for (int li = 0; li < kFmLB; ++li) {
                 const int l = l0 + li;
