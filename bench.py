@@ -33,6 +33,7 @@ HW = 832
 N_IMAGES = 8
 METRIC = "image-pairs/s coarse-match (hp2: tracks/s refinement)"
 NOISE = 0.025
+STAGGER_MS = float(os.environ.get("DFSFM_BENCH_STAGGER_MS", "0"))   # experiment knob: start pair worker w this many ms x w after worker 0
 WORKLOAD = (f"C2 demo scene: {N_IMAGES} overlapping synthetic views {HW}x{HW} (crops of one low-pass noise image at 8-px-aligned offsets + "
             f"N(0,{NOISE}) per view), exhaustive 28 pairs per rank, LoFTR coarse_only, shipped thr 0.2 / temperature 0.1, BN-calibrated "
             "seeded weights (tests/weights.py) -> O(10^3) matches per pair; the step ends with the match->keypoint merge of its own matches")
@@ -380,6 +381,8 @@ def main():
     def run_pairs(widx, todo, cached, out):
         mw, stream = workers[widx]
         torch.cuda.set_device(local)
+        if widx and STAGGER_MS > 0:
+            time.sleep(widx * STAGGER_MS / 1000.0)
         with torch.cuda.stream(stream):
             for k in todo:
                 i, j = pairs[k]
