@@ -33,7 +33,6 @@ HW = 832
 N_IMAGES = 8
 METRIC = "image-pairs/s coarse-match (hp2: tracks/s refinement)"
 NOISE = 0.025
-STAGGER_MS = float(os.environ.get("DFSFM_BENCH_STAGGER_MS", "0"))   # experiment knob: start pair worker w this many ms x w after worker 0
 WORKLOAD = (f"C2 demo scene: {N_IMAGES} overlapping synthetic views {HW}x{HW} (crops of one low-pass noise image at 8-px-aligned offsets + "
             f"N(0,{NOISE}) per view), exhaustive 28 pairs per rank, LoFTR coarse_only, shipped thr 0.2 / temperature 0.1, BN-calibrated "
             "seeded weights (tests/weights.py) -> O(10^3) matches per pair; the step ends with the match->keypoint merge of its own matches")
@@ -377,12 +376,13 @@ def main():
         mw = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=2 * N_IMAGES).cuda(local).eval()
         mw.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
         workers.append((mw, torch.cuda.Stream(device=dev)))
+    from detectorfreesfm_b200.coarse_stage import pool_thread_begin, pool_thread_end, share_backbone_baton
+    baton = share_backbone_baton([w[0] for w in workers])   # what coarse_stage.match_workers does for its pool
 
     def run_pairs(widx, todo, cached, out):
         mw, stream = workers[widx]
         torch.cuda.set_device(local)
-        if widx and STAGGER_MS > 0:
-            time.sleep(widx * STAGGER_MS / 1000.0)
+        pool_thread_begin(n_workers)
         with torch.cuda.stream(stream):
             for k in todo:
                 i, j = pairs[k]
@@ -391,6 +391,7 @@ def main():
                     data["pair_key"] = ((f"im{i}",), (f"im{j}",))
                 mw(data)
                 out[k] = torch.cat([data["mkpts0_f"], data["mkpts1_f"], data["mconf"][:, None]], -1)
+        pool_thread_end()
 
     def step_resident(cached):
         """inputs resident in HBM; returns the per-pair (M,5) device arrays"""
@@ -426,6 +427,7 @@ def main():
         (M,5) match array back to the host -- on the worker's own stream"""
         mw, stream = workers[widx]
         torch.cuda.set_device(local)
+        pool_thread_begin(n_workers)
         up = down = 0
         with torch.cuda.stream(stream):
             for k in todo:
@@ -441,6 +443,7 @@ def main():
                 m = md.cpu().numpy()
                 down += m.nbytes + 4  # + the match-count readback that sizes the arrays
                 res[k] = m
+        pool_thread_end()
         counts[widx] = (up, down)
 
     def step_e2e(cached):
@@ -740,7 +743,7 @@ def main():
                        "l2": "per-step working set (activations of one 832x832 image ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "backbone": "run for both images of every pair in `value`/`e2e` (as the reference does); *_cached keys use the exact per-image feature cache",
                        "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays",
-                       "pair_workers_per_gpu": n_workers},
+                       "pair_workers_per_gpu": n_workers, "backbone_baton": baton is not None},
             "value_cached": n_pairs * K / (ms_cached * 1e-3),
             "value_one_pair_in_flight": (n_pairs * K / (ms_cold_1w * 1e-3)) if ms_cold_1w else None,
             "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

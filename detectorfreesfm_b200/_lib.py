@@ -15,6 +15,7 @@ PROTOTYPES = {
     "dfsfm_last_error": (c_char_p, []),
     "dfsfm_version": (c_int, []),
     "dfsfm_launch_count": (c_int64, []),
+    "dfsfm_thread_set_pdl": (None, [c_int]),
     "dfsfm_debug_gemm_slab": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                                       c_int, c_int, c_void_p]),
     "dfsfm_set_engine": (None, [c_int]),

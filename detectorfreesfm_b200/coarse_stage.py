@@ -11,8 +11,13 @@ Mirrors ``match_worker`` (src/coarse_match/coarse_match_worker.py:103-145: datas
 Nothing leaves the GPU between the decoded uint8 image and the final keypoint / match-index arrays except the dict
 bookkeeping; the outputs have the reference's types, so ``save_h5`` (coarse_match.py:239-256) applies unchanged.
 """
+import os
+import threading
+
 import torch
 
+from . import _lib
+from .coarse_matcher import BackboneBaton
 from .image_pipeline import B200CoarseMatchingDataset
 from .postprocess import KeypointMerger
 
@@ -50,15 +55,99 @@ def match_worker(subset_ids, image_lists, covis_pairs_out, cfgs, matcher, detect
     return matches
 
 
+def share_backbone_baton(matchers, enable=None):
+    """Give the pair workers of one GPU a common BackboneBaton (matchers without the attribute -- foreign models -- are left alone).
+    ``DFSFM_BACKBONE_BATON=0`` turns the ordering off (A/B)."""
+    if enable is None:
+        enable = os.environ.get("DFSFM_BACKBONE_BATON", "1") != "0"
+    baton = BackboneBaton() if (enable and len(matchers) > 1) else None
+    for m in matchers:
+        if hasattr(m, "backbone_baton"):
+            m.backbone_baton = baton
+    return baton
+
+
+def pool_thread_begin(n_workers):
+    """Called by a host thread before it drives one of ``n_workers`` pair workers of a GPU: programmatic dependent launch off for this
+    thread's launches when n_workers > 1 (include/dfsfm_b200.h ``dfsfm_thread_set_pdl``; DFSFM_POOL_PDL=1 keeps it on, A/B)."""
+    if n_workers > 1 and os.environ.get("DFSFM_POOL_PDL", "0") != "1":
+        _lib.load_library().dfsfm_thread_set_pdl(0)
+
+
+def pool_thread_end():
+    _lib.load_library().dfsfm_thread_set_pdl(-1)
+
+
+def match_workers(all_subset_ids, image_lists, covis_pairs_out, cfgs, matchers, detector=None, keep_on_device=False, datasets=None):
+    """coarse_match.py:126-140 on ONE GPU: the reference deals the pair ids into ``n_workers`` subsets (``chunk_index``), runs one Ray
+    actor -- its own model, ``n_gpus_per_worker`` of a GPU -- per subset and ChainMaps the result dicts.  Here every subset gets one
+    host thread driving ``match_worker`` with its OWN matcher (own engine handle and workspaces) on its OWN CUDA stream of the current
+    device; the threads spend their time inside the C ABI and CUDA calls (GIL released), so the pairs of different workers overlap on the
+    GPU.  At 832x832 a single pair leaves ~40 % of the SMs idle in the transformer (43 / 86 tiles for 74 CTA pairs, DESIGN.md section
+    6); two workers measured +18 % pairs/s, three +24 %.
+
+    ``matchers``: one per subset (e.g. ``[build_model(cfg) for _ in range(n)]``).  ``datasets``: optional, one per subset.
+    Results are identical to one worker's (every pair is computed independently); key collisions resolve like ``dict(ChainMap(*results))``.
+    """
+    n = len(all_subset_ids)
+    assert len(matchers) == n and (datasets is None or len(datasets) == n)
+    assert len({id(m) for m in matchers}) == n, "every worker needs its own matcher (workspaces are per engine handle)"
+    share_backbone_baton(matchers)
+    dev = torch.cuda.current_device()
+    main = torch.cuda.current_stream(dev)
+    streams = [main] + [torch.cuda.Stream(dev) for _ in range(n - 1)]
+    start = torch.cuda.Event()
+    start.record(main)
+    results, errors = [None] * n, [None] * n
+
+    def run(w):
+        try:
+            torch.cuda.set_device(dev)
+            pool_thread_begin(n)
+            streams[w].wait_event(start)
+            with torch.cuda.stream(streams[w]):
+                results[w] = match_worker(all_subset_ids[w], image_lists, covis_pairs_out, cfgs, matchers[w], detector=detector,
+                                          keep_on_device=keep_on_device, dataset=None if datasets is None else datasets[w])
+        except BaseException as e:  # re-raised in the calling thread
+            errors[w] = e
+        finally:
+            pool_thread_end()
+
+    threads = [threading.Thread(target=run, args=(w,)) for w in range(1, n)]
+    for t in threads:
+        t.start()
+    run(0)
+    for t in threads:
+        t.join()
+    for w in range(1, n):
+        main.wait_stream(streams[w])
+    for e in errors:
+        if e is not None:
+            raise e
+    merged = {}
+    for w in range(n - 1, -1, -1):           # ChainMap: the first mapping wins
+        if keep_on_device and w > 0:
+            for v in results[w].values():    # allocated on the worker's stream, consumed on the caller's
+                v.record_stream(main)
+        merged.update(results[w])
+    return merged
+
+
 def coarse_matching_stage(image_lists, covis_pairs, cfgs, matcher, detector=None, merger=None):
     """coarse_match.py:190-237 without Ray and without the h5 cache: all pairs -> (final_keypoints, final_scores,
-    updated_matches, raw matches).  ``covis_pairs``: list of "path0 path1" strings or a file of them."""
+    updated_matches, raw matches).  ``covis_pairs``: list of "path0 path1" strings or a file of them.  ``matcher``: one matcher, or a
+    list of them = that many pair workers on this GPU (``match_workers``)."""
     if isinstance(covis_pairs, list):
         pair_list = covis_pairs
     else:
         with open(covis_pairs, "r") as f:
             pair_list = f.read().rstrip("\n").split("\n")
-    matches = match_worker(list(range(len(pair_list))), image_lists, pair_list, cfgs, matcher, detector=detector, keep_on_device=True)
+    if isinstance(matcher, (list, tuple)) and len(matcher) > 1:    # several workers on this GPU (ray n_workers / n_gpus_per_worker < 1)
+        subsets = [list(range(w, len(pair_list), len(matcher))) for w in range(len(matcher))]
+        matches = match_workers(subsets, image_lists, pair_list, cfgs, list(matcher), detector=detector, keep_on_device=True)
+    else:
+        one = matcher[0] if isinstance(matcher, (list, tuple)) else matcher
+        matches = match_worker(list(range(len(pair_list))), image_lists, pair_list, cfgs, one, detector=detector, keep_on_device=True)
     merger = merger if merger is not None else KeypointMerger()
     final_keypoints, final_scores, updated_matches = merger(matches, image_lists, cfgs["matcher"]["pair_name_split"])
     return final_keypoints, final_scores, updated_matches, matches

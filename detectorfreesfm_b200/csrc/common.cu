@@ -113,6 +113,7 @@ extern "C" {
 const char* dfsfm_last_error(void) { return dfsfm::g_last_error.c_str(); }
 int dfsfm_version(void) { return 1; }
 int64_t dfsfm_launch_count(void) { return dfsfm::launch_counter().load(); }
+void dfsfm_thread_set_pdl(int mode) { dfsfm::pdl_thread_override() = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 void dfsfm_set_engine(int version) { dfsfm::set_engine_version(version); }
 int dfsfm_get_engine(void) { return dfsfm::engine_version(); }

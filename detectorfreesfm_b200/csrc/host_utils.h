@@ -135,7 +135,17 @@ inline int sm_count() {
     }
     return v;
 }
+// Programmatic dependent launch: on by default (the next kernel's prologue overlaps the tail of the previous one: +3 % with one pair in
+// flight).  With several pair workers per GPU it costs throughput -- the early-resident CTAs of a dependent launch hold SMs (200+ KB of
+// shared memory each) that another worker's ready kernel could use: 233 -> 250 pairs/s with it off at two workers -- so a worker thread
+// of a pool turns it off for its own launches (dfsfm_thread_set_pdl).  -1 = the process default (DFSFM_PDL, on).
+inline int& pdl_thread_override() {
+    static thread_local int v = -1;
+    return v;
+}
 inline bool pdl_enabled() {
+    const int o = pdl_thread_override();
+    if (o >= 0) return o == 1;
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DFSFM_PDL");

@@ -165,6 +165,10 @@ int dfsfm_debug_timeline_arm(int max_launches);
 int dfsfm_debug_timeline_read(uint64_t* stamps, int32_t* info, int max_launches);
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 int64_t dfsfm_launch_count(void);
+/* Programmatic dependent launch for the launches made from the CALLING host thread: 1 on, 0 off, -1 the process default (on; DFSFM_PDL=0
+ * turns it off).  A pair worker of a several-workers-per-GPU pool (coarse_match.py:49-55, n_gpus_per_worker 0.5) turns it off: early-resident
+ * dependent CTAs would hold SMs another worker's kernel could use. */
+void dfsfm_thread_set_pdl(int mode);
 
 #ifdef __cplusplus
 }

@@ -63,3 +63,47 @@ def test_coarse_matching_stage_matches_oracle_chain(tmp_path):
     m_np = match_worker([0, 1, 2], paths, pairs, cfgs, matcher)
     assert all(isinstance(v, np.ndarray) and v.dtype == np.float32 and np.array_equal(v, raw[k].cpu().numpy()) for k, v in m_np.items())
     assert n_total > 10
+
+
+def test_pair_workers_on_one_gpu_give_the_single_worker_result(tmp_path):
+    """coarse_match.py:126-140 (n_workers Ray actors, ChainMap of their dicts) as host threads with one matcher + stream each on one GPU:
+    bit-identical to the single worker, for the worker loop and for the whole stage."""
+    import cv2
+    from detectorfreesfm_b200 import B200LoFTR
+    from detectorfreesfm_b200.coarse_stage import coarse_matching_stage, match_worker, match_workers
+    from tests import weights
+    from tests import util
+
+    sd = weights.loftr_state_dict(0, calibrated=True)
+    images, _ = util.synth_scene(5, 160, 208, seed=77, noise=0.025, max_shift=32)
+    paths = []
+    for i, im in enumerate(images):
+        p = str(tmp_path / f"v{i}.png")
+        assert cv2.imwrite(p, (im[0, 0].numpy() * 255).astype(np.uint8))
+        paths.append(p)
+    pairs = [f"{paths[a]} {paths[b]}" for a in range(5) for b in range(a + 1, 5)]
+    cfgs = {"data": {"img_resize": 208, "df": 8, "pad_to": None, "img_preload": False, "img_type": "grayscale"},
+            "matcher": {"model": {"type": "coarse_only"}, "round_matches_ratio": None, "pair_name_split": " "}}
+
+    def build():
+        m = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1)).cuda().eval()
+        m.load_state_dict(sd)
+        return m
+
+    ms = [build() for _ in range(3)]
+    one = match_worker(list(range(len(pairs))), paths, pairs, cfgs, ms[0])
+    assert sum(v.shape[0] for v in one.values()) > 100
+    for n in (2, 3):
+        subsets = [list(range(w, len(pairs), n)) for w in range(n)]
+        many = match_workers(subsets, paths, pairs, cfgs, ms[:n])
+        assert list(sorted(many)) == list(sorted(one))
+        assert all(np.array_equal(many[k], one[k]) for k in one)
+        dev = match_workers(subsets, paths, pairs, cfgs, ms[:n], keep_on_device=True)
+        torch.cuda.synchronize()
+        assert all(np.array_equal(dev[k].cpu().numpy(), one[k]) for k in one)
+    k1, s1, u1, _ = coarse_matching_stage(paths, pairs, cfgs, ms[0])
+    k2, s2, u2, _ = coarse_matching_stage(paths, pairs, cfgs, ms[:2])
+    assert all(np.array_equal(k1[p], k2[p]) and np.array_equal(s1[p], s2[p]) for p in paths)
+    assert all(np.array_equal(u1[k], u2[k]) for k in pairs)
+    with pytest.raises(AssertionError):
+        match_workers([[0], [1]], paths, pairs, cfgs, [ms[0], ms[0]])     # one engine handle cannot serve two threads
