@@ -376,8 +376,7 @@ def main():
         mw = B200LoFTR(util.loftr_config(thr=0.2, temperature=0.1), feature_cache_size=2 * N_IMAGES).cuda(local).eval()
         mw.load_state_dict(weights.loftr_state_dict(0, calibrated=True))
         workers.append((mw, torch.cuda.Stream(device=dev)))
-    from detectorfreesfm_b200.coarse_stage import pool_thread_begin, pool_thread_end, share_backbone_baton
-    baton = share_backbone_baton([w[0] for w in workers])   # what coarse_stage.match_workers does for its pool
+    from detectorfreesfm_b200.coarse_stage import pool_thread_begin, pool_thread_end   # what coarse_stage.match_workers does per thread
 
     def run_pairs(widx, todo, cached, out):
         mw, stream = workers[widx]
@@ -743,7 +742,7 @@ def main():
                        "l2": "per-step working set (activations of one 832x832 image ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "backbone": "run for both images of every pair in `value`/`e2e` (as the reference does); *_cached keys use the exact per-image feature cache",
                        "parallelism": f"pairs sharded over {world} rank(s), one scene per rank, final gather of (M,5) arrays",
-                       "pair_workers_per_gpu": n_workers, "backbone_baton": baton is not None},
+                       "pair_workers_per_gpu": n_workers},
             "value_cached": n_pairs * K / (ms_cached * 1e-3),
             "value_one_pair_in_flight": (n_pairs * K / (ms_cold_1w * 1e-3)) if ms_cold_1w else None,
             "e2e": {"value": n_pairs * K / (ms_e2e * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

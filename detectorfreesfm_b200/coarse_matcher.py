@@ -7,26 +7,12 @@ libdfsfm_b200.so (hand-written sm_100a CUDA); this file only moves pointers and 
 (the backbone is exact per image because BatchNorm is in eval mode, so features are reusable across pairs).
 """
 import ctypes
-import threading
 from collections import OrderedDict
 
 import torch
 
 from . import _lib
 from .packing import pack_loftr, position_encoding
-
-
-class BackboneBaton:
-    """Shared by the pair workers of ONE GPU (coarse_stage.match_workers): orders their backbone phases on the device.
-
-    The backbone launches are persistent 148-CTA kernels, the transformer launches offer 43 / 86 tiles to 74 CTA pairs.  Two workers that
-    drift into the SAME phase gain nothing from each other (two full-GPU kernels time-slice; two 43-cluster launches need 86 of 74 slots,
-    i.e. two rounds) -- measured as a bimodal 192-235 pairs/s at 832x832.  With the baton a worker's backbone waits (stream-side, an
-    event) for the previous worker's backbone, so one worker's transformer / similarity phase always runs beside another's backbone."""
-
-    def __init__(self):
-        self.lock = threading.Lock()
-        self.event = None
 
 
 class B200LoFTR(torch.nn.Module):
@@ -62,7 +48,6 @@ class B200LoFTR(torch.nn.Module):
         self._cache_bytes_max = int(feature_cache_bytes)
         self._cache_bytes = 0
         self._packed = None
-        self.backbone_baton = None   # a BackboneBaton when this matcher is one of several pair workers of a GPU
         if device is not None:
             self.cuda(device)
 
@@ -209,19 +194,8 @@ class B200LoFTR(torch.nn.Module):
         if names is not None:
             k0 = names[0][0] if isinstance(names[0], (list, tuple)) else names[0]
             k1 = names[1][0] if isinstance(names[1], (list, tuple)) else names[1]
-        baton = self.backbone_baton
-        if baton is None:
-            f0 = self.extract_features(im0, k0)
-            f1 = self.extract_features(im1, k1)
-        else:
-            with baton.lock:
-                st = torch.cuda.current_stream(im0.device)
-                if baton.event is not None:
-                    st.wait_event(baton.event)
-                f0 = self.extract_features(im0, k0)
-                f1 = self.extract_features(im1, k1)
-                baton.event = torch.cuda.Event()
-                baton.event.record(st)
+        f0 = self.extract_features(im0, k0)
+        f1 = self.extract_features(im1, k1)
         if self.fine:
             (f0, ff0), (f1, ff1) = f0, f1
         hw0_c = (im0.shape[2] // 8, im0.shape[3] // 8)

@@ -17,7 +17,6 @@ import threading
 import torch
 
 from . import _lib
-from .coarse_matcher import BackboneBaton
 from .image_pipeline import B200CoarseMatchingDataset
 from .postprocess import KeypointMerger
 
@@ -55,18 +54,6 @@ def match_worker(subset_ids, image_lists, covis_pairs_out, cfgs, matcher, detect
     return matches
 
 
-def share_backbone_baton(matchers, enable=None):
-    """Give the pair workers of one GPU a common BackboneBaton (matchers without the attribute -- foreign models -- are left alone).
-    ``DFSFM_BACKBONE_BATON=0`` turns the ordering off (A/B)."""
-    if enable is None:
-        enable = os.environ.get("DFSFM_BACKBONE_BATON", "1") != "0"
-    baton = BackboneBaton() if (enable and len(matchers) > 1) else None
-    for m in matchers:
-        if hasattr(m, "backbone_baton"):
-            m.backbone_baton = baton
-    return baton
-
-
 def pool_thread_begin(n_workers):
     """Called by a host thread before it drives one of ``n_workers`` pair workers of a GPU: programmatic dependent launch off for this
     thread's launches when n_workers > 1 (include/dfsfm_b200.h ``dfsfm_thread_set_pdl``; DFSFM_POOL_PDL=1 keeps it on, A/B)."""
@@ -84,7 +71,8 @@ def match_workers(all_subset_ids, image_lists, covis_pairs_out, cfgs, matchers, 
     host thread driving ``match_worker`` with its OWN matcher (own engine handle and workspaces) on its OWN CUDA stream of the current
     device; the threads spend their time inside the C ABI and CUDA calls (GIL released), so the pairs of different workers overlap on the
     GPU.  At 832x832 a single pair leaves ~40 % of the SMs idle in the transformer (43 / 86 tiles for 74 CTA pairs, DESIGN.md section
-    6); two workers measured +18 % pairs/s, three +24 %.
+    6); two workers measured +18 % pairs/s, three +24 %.  (Ordering the workers' backbone phases with events -- one worker's backbone
+    always beside another's transformer -- was tried and measured WORSE, 204-243 vs 229-255 pairs/s: profiles/r02_worker_pool.txt.)
 
     ``matchers``: one per subset (e.g. ``[build_model(cfg) for _ in range(n)]``).  ``datasets``: optional, one per subset.
     Results are identical to one worker's (every pair is computed independently); key collisions resolve like ``dict(ChainMap(*results))``.
@@ -92,7 +80,6 @@ def match_workers(all_subset_ids, image_lists, covis_pairs_out, cfgs, matchers, 
     n = len(all_subset_ids)
     assert len(matchers) == n and (datasets is None or len(datasets) == n)
     assert len({id(m) for m in matchers}) == n, "every worker needs its own matcher (workspaces are per engine handle)"
-    share_backbone_baton(matchers)
     dev = torch.cuda.current_device()
     main = torch.cuda.current_stream(dev)
     streams = [main] + [torch.cuda.Stream(dev) for _ in range(n - 1)]

@@ -55,7 +55,7 @@ struct GemmCore {
 };
 
 __device__ __forceinline__ void tl_stamp(const GemmCore& core, int ev) {
-    if (core.tl != nullptr) {
+    if (core.tl != nullptr && blockIdx.x < 148) {  // the host buffer holds 148 CTAs per launch
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         core.tl[blockIdx.x * 16 + ev] = t;
@@ -207,12 +207,13 @@ struct Gemm2Cfg {
     // per-warp epilogue staging (Epi::kEpiStageBytes: the warp's 32-row block is transposed through shared memory so that global
     // loads / stores of the epilogue are row-contiguous); it comes out of the operand-stage budget only when it has to
     static constexpr int kEpiSmem = kEpiStageBytes * kGemm2EpiWarps;
-    static constexpr int kBudgetMax = 227 * 1024 - 1024 - 256 - kEpiSmem;
+    static constexpr int kBarBytes = 768;  // pipeline barriers, TMEM slot, cluster-launch-control answers + their barriers
+    static constexpr int kBudgetMax = 227 * 1024 - 1024 - kBarBytes - kEpiSmem;
     static constexpr int kBudget = kBudgetMax < 204 * 1024 ? kBudgetMax : 204 * 1024;
     static constexpr int kStagesRaw = kBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-    static constexpr int kEpiOff = kStages * kStageBytes + 256;  // after the barriers
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kEpiSmem;
+    static constexpr int kEpiOff = kStages * kStageBytes + kBarBytes;  // after the barriers
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + kBarBytes + kEpiSmem;
     static constexpr int kAccCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     // kSepCorr: hi*lo + lo*hi go to their own accumulator (long-K convolutions).  Short-K linears fold them into the main
     // accumulator (truncation bias ~ -5.5e-9*K*3 relative: harmless at K <= 512), which leaves TMEM room for a second
@@ -231,6 +232,49 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, 
     return d;
 }
 
+// Tile order of a cluster.  Static: tile = cluster + k * clusters with min(tiles, SM pairs) clusters in the grid.  Stealing: the grid has
+// ONE cluster per tile; while a cluster works on a tile its producer asks the hardware to cancel a cluster of the grid that has not been
+// launched yet (cluster launch control) and the whole cluster takes that tile next, until nothing is left to cancel.  Clusters that start
+// late -- SMs held by another stream's kernel (several pair workers per GPU), or by the tail of the previous kernel of this stream under
+// programmatic dependent launch -- then simply take fewer tiles instead of stretching the launch by their static share.
+// The answers go through a ring of kClcSlots slots without "empty" barriers: the producer of a cluster is never more than kStages
+// K-chunks ahead of the MMA thread and that at most two accumulator sets ahead of the slowest epilogue warp, far fewer than 16 tiles.
+constexpr int kClcSlots = 16;
+struct TileSched {
+    uint64_t* bars;  // [kClcSlots], this CTA's
+    uint4* resp;     // [kClcSlots]
+    int num_tiles, num_clusters;
+    bool steal;
+    int j, tile;
+    __device__ __forceinline__ int first() {
+        j = 0;
+        tile = blockIdx.x >> 1;
+        return tile;
+    }
+    // the producer thread of each CTA, at the start of its tile j: arm the slot; CTA 0 also sends the request whose answer is tile j + 1
+    __device__ __forceinline__ void request(uint32_t rank) {
+        if (steal) {
+            const int q = j & (kClcSlots - 1);
+            mbar_arrive_expect_tx(&bars[q], 16);
+            if (rank == 0) clc_try_cancel_multicast(&resp[q], &bars[q]);
+        }
+    }
+    __device__ __forceinline__ int next() {
+        if (steal) {
+            const int q = j & (kClcSlots - 1);
+            mbar_wait(&bars[q], (j / kClcSlots) & 1);
+            const int x = clc_decode(&resp[q]);
+            fence_proxy_async();  // this generic read before the slot's next asynchronous write
+            tile = x < 0 ? -1 : (x >> 1);
+        } else {
+            tile += num_clusters;
+            if (tile >= num_tiles) tile = -1;
+        }
+        ++j;
+        return tile;
+    }
+};
+
 struct EpiNoState {};
 template <class Epi, bool = Epi::kHasState>
 struct EpiStateOf { using type = EpiNoState; };
@@ -240,7 +284,7 @@ struct EpiStateOf<Epi, true> { using type = typename Epi::State; };
 template <int BN, bool kSplit, class Epi, int G = 1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemm2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, const typename Epi::Params ep, const int num_tiles,
-                const int n_tiles) {
+                const int n_tiles, const int steal) {
     using Cfg = Gemm2Cfg<BN, kSplit, Epi::kSeparateCorr, G, Epi::kEpiStageBytes>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -249,6 +293,9 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* clc_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
+    uint4* clc_resp = reinterpret_cast<uint4*>(clc_bar + kClcSlots);
+    static_assert(256 + kClcSlots * (8 + 16) <= Cfg::kBarBytes && (2 * 6 + 4) * 8 + 4 <= 256, "barrier region");
 
     // Programmatic dependent launch: let the next kernel of the stream start its prologue on SMs we leave idle ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -270,6 +317,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             mbar_init(&tmem_full_bar[a], 1);
             mbar_init(&tmem_empty_bar[a], 2 * kGemm2EpiWarps);  // every epilogue warp of both CTAs arrives on the leader's barrier
         }
+        for (int q = 0; q < kClcSlots; ++q) mbar_init(&clc_bar[q], 1);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_slot);
@@ -282,12 +330,19 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (threadIdx.x == 0) tl_stamp(core, 2);
     const int n_iters = (core.num_taps / G) * core.kchunks;
+    TileSched ts;
+    ts.bars = clc_bar;
+    ts.resp = clc_resp;
+    ts.num_tiles = num_tiles;
+    ts.num_clusters = num_clusters;
+    ts.steal = steal != 0;
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0;
             uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int tile = ts.first(); tile >= 0; tile = ts.next()) {
+                ts.request(rank);
                 const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
                 const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
                 const int nrow = core.b_row0 + nt * BN + static_cast<int>(rank) * (BN / 2) + ((core.seg_mp0 > 0 && mp >= core.seg_mp0) ? core.seg_b_rows : 0);
@@ -320,7 +375,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
             uint32_t phase = 0;
             int a = 0;
             uint32_t aphase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            for (int tile = ts.first(); tile >= 0; tile = ts.next()) {
                 mbar_wait(&tmem_empty_bar[a], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_acc = tmem_base + a * Cfg::kSetCols;
@@ -330,7 +385,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     const int c = it % core.kchunks;
                     mbar_wait(&full_bar[s], phase);
                     tc_fence_after();
-                    if (it == 0 && tile == cluster_id) tl_stamp(core, 3);
+                    if (it == 0 && ts.j == 0) tl_stamp(core, 3);
                     const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
                     const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
@@ -355,7 +410,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     if (++s == Cfg::kStages) { s = 0; phase ^= 1; }
                 }
                 umma_commit_2sm(&tmem_full_bar[a]);
-                tl_stamp(core, tile == cluster_id ? 4 : 5);  // MMAs of the first / of the latest tile issued
+                tl_stamp(core, ts.j == 0 ? 4 : 5);  // MMAs of the first / of the latest tile issued
                 if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
             }
         }
@@ -374,12 +429,12 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
         // stateful epilogues (KvEpi) carry per-thread accumulators across the tiles of this persistent CTA
         typename EpiStateOf<Epi>::type est;
         if constexpr (Epi::kHasState) Epi::init(est);
-        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        for (int tile = ts.first(); tile >= 0; tile = ts.next()) {
             const int mp = tile / n_tiles, nt = tile - mp * n_tiles;
             const int m0 = (mp * 2 + static_cast<int>(rank)) * kBM;
             mbar_wait(&tmem_full_bar[a], aphase);
             tc_fence_after();
-            if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 6 : 8);  // accumulator of the first / latest tile complete
+            if (warp == 2 && lane == 0) tl_stamp(core, ts.j == 0 ? 6 : 8);  // accumulator of the first / latest tile complete
             if constexpr (Epi::kHasState)
                 Epi::template run_state<BN>(ep, est, tmem_base + a * Cfg::kSetCols + (static_cast<uint32_t>(quad * 32) << 16), m0 + quad * 32, lane, nt,
                                             half, quad, ctx, smem + Cfg::kEpiOff);
@@ -388,7 +443,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                                                      nt * BN, cb, ce, nt * 2 + half, ctx);
             tc_fence_before();
             __syncwarp();
-            if (warp == 2 && lane == 0) tl_stamp(core, tile == cluster_id ? 7 : 9);  // epilogue of the first / latest tile done (this warp)
+            if (warp == 2 && lane == 0) tl_stamp(core, ts.j == 0 ? 7 : 9);  // epilogue of the first / latest tile done (this warp)
             if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
             if (++a == Cfg::kAccStages) { a = 0; aphase ^= 1; }
         }

@@ -143,6 +143,14 @@ inline int& pdl_thread_override() {
     static thread_local int v = -1;
     return v;
 }
+inline bool tile_steal_enabled() {  // DFSFM_TILE_STEAL=0: static round-robin tiles on min(tiles, SM pairs) persistent clusters (A/B)
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("DFSFM_TILE_STEAL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
 inline bool pdl_enabled() {
     const int o = pdl_thread_override();
     if (o >= 0) return o == 1;
@@ -185,7 +193,9 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
     const int n_tiles = (n_total + BN - 1) / BN;
     const int tiles = m_pairs * n_tiles;
     const int max_clusters = sm_count() / 2;
-    const int clusters = tiles < max_clusters ? tiles : max_clusters;
+    // stateless epilogues: one cluster per tile, running clusters steal the tiles of clusters not yet launched (gemm_engine.cuh TileSched)
+    const bool steal = !Epi::kHasState && tile_steal_enabled() && tiles > max_clusters;
+    const int clusters = (steal || tiles < max_clusters) ? tiles : max_clusters;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * clusters);
@@ -198,10 +208,10 @@ inline void launch_gemm2(const TmapPack& maps, const GemmCore& core, const typen
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     GemmCore core_l = core;
-    core_l.tl = timeline_next_launch(2 * clusters, tiles);
+    core_l.tl = timeline_next_launch(2 * clusters < 148 ? 2 * clusters : 148, tiles);
     typename Epi::Params ep_l = ep;
     set_debug(ep_l);
-    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, core_l, ep_l, tiles, n_tiles));
+    DFSFM_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, core_l, ep_l, tiles, n_tiles, steal ? 1 : 0));
 }
 
 // Fill the tap table of a stride-1 k x k convolution on a flat-halo geometry with row pitch Wp.

@@ -45,6 +45,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// ------------------------------------------------------------------- cluster launch control (work stealing)
+// One thread of CTA 0 of a cluster asks the hardware to cancel a not-yet-launched cluster of this grid; the 16-byte answer lands at the same
+// shared-memory offset in EVERY CTA of the requesting cluster and completes 16 bytes on the mbarrier at `bar`'s offset in each of them.
+__device__ __forceinline__ void clc_try_cancel_multicast(void* resp, uint64_t* bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                 ::"r"(smem_u32(resp)), "r"(smem_u32(bar)) : "memory");
+}
+// -> blockIdx.x of the first CTA of the cancelled cluster (its work is now ours), or -1 when nothing was left to cancel.
+__device__ __forceinline__ int clc_decode(const void* resp) {
+    uint32_t valid, x;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 c;\n\t.reg .b32 y, z;\n\t"
+        "ld.shared.b128 c, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, c;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, y, z, _}, c;\n\t}"
+        : "=r"(x), "=r"(valid) : "r"(smem_u32(resp)) : "memory");
+    return valid ? static_cast<int>(x) : -1;
+}
+
 // ---------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
