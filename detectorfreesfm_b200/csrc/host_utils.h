@@ -143,11 +143,15 @@ inline int& pdl_thread_override() {
     static thread_local int v = -1;
     return v;
 }
-inline bool tile_steal_enabled() {  // DFSFM_TILE_STEAL=0: static round-robin tiles on min(tiles, SM pairs) persistent clusters (A/B)
+// DFSFM_TILE_STEAL=1: one cluster per tile and cluster-launch-control work stealing (gemm_engine.cuh TileSched) instead of the static
+// round-robin tile order on min(tiles, SM pairs) persistent clusters.  Off by default: measured neutral on B200 (three pair workers 255.5 /
+// 256.0 vs 256.9 / 256.1 pairs/s, conv launches 66.8-67.1 ms per step either way; profiles/r02_worker_pool.txt) -- uniform tiles leave
+// nothing to balance and a late cluster costs little next to 9+ tiles per cluster.
+inline bool tile_steal_enabled() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("DFSFM_TILE_STEAL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0] == '1') ? 1 : 0;
     }
     return v == 1;
 }

@@ -160,3 +160,17 @@ def test_transformer_schedules_agree_with_oracle(env):
     e.update(env)
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "check_transformer.py")], env=e, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_tile_stealing_schedule_meets_the_same_parity_bar():
+    """DFSFM_TILE_STEAL=1 (cluster-launch-control work stealing in the engine-2 GEMM, off by default) on the C1 shape, where the conv and
+    similarity launches have 4-25 tiles per CTA pair: the BASELINE-shape oracle test in a subprocess (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e["DFSFM_TILE_STEAL"] = "1"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_baseline_shapes_gpu.py"), "-m", "gpu", "-q", "-x",
+                        "-k", "shipped_config and hw0"], env=e, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
