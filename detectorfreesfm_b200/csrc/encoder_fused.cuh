@@ -31,7 +31,7 @@ constexpr int kEncChunk = 32 * 1024;            // one 64-wide K chunk of a 128-
 constexpr int kEncAct = 4 * kEncChunk;
 constexpr int kEncRingStages = 3;
 constexpr int kEncBarOff = kEncAct + kEncRingStages * kEncChunk;
-constexpr int kEncLnxOff = kEncBarOff + 256;    // LayerNorm-1 statistics exchange: 8 warps x 256 B
+constexpr int kEncLnxOff = kEncBarOff + 512;    // LayerNorm-1 statistics exchange: 8 warps x 256 B
 constexpr int kEncSmemBytes = kEncLnxOff + 8 * 256;
 static_assert(kEncSmemBytes <= 227 * 1024, "fused encoder layer: shared memory budget");
 
@@ -111,13 +111,17 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
     uint64_t* out_done = bars + 14;
     uint64_t* g4_done = bars + 15;
     uint64_t* g3m_done = bars + 16;
-    uint64_t* qp_ready = bars + 17;     // epilogue warps of both CTAs -> leader (16 arrivals)
-    uint64_t* m_ready = bars + 18;
-    uint64_t* hid_ready = bars + 19;    // [2]
-    uint64_t* e4_done = bars + 21;      // epilogue warps of both CTAs -> BOTH CTAs (16 arrivals each)
-    uint64_t* xr_full = bars + 22;      // residual x tile landed in act (per CTA, local TMA)
-    uint64_t* x0_done = bars + 23;      // MMA commit: the x part of mlp.0 chunk 0 has read x from act (the epilogue may overwrite it with m)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    // epilogue -> MMA hand-offs, one barrier per 64-column K chunk of the consuming GEMM: a chunk belongs to one column half, i.e. to the
+    // four quad warps of that half in both CTAs (8 arrivals on the leader's barrier).  The consuming GEMM takes the chunks in the order
+    // 0, 2, 1, 3 -- both halves finish their first chunk at the same time -- so its first K steps run under the rest of the epilogue.
+    uint64_t* qp_ready = bars + 17;     // [4]
+    uint64_t* m_ready = bars + 21;      // [4]
+    uint64_t* hid_ready = bars + 25;    // [2][4]
+    uint64_t* e4_done = bars + 33;      // epilogue warps of both CTAs -> BOTH CTAs (16 arrivals each)
+    uint64_t* xr_full = bars + 34;      // residual x tile landed in act (per CTA, local TMA)
+    uint64_t* x0_done = bars + 35;      // MMA commit: the x part of mlp.0 chunk 0 has read x from act (the epilogue may overwrite it with m)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+    auto chunk_order = [](int i) { return ((i & 1) << 1) | (i >> 1); };   // 0, 2, 1, 3
     float* lnx = reinterpret_cast<float*>(smem + kEncLnxOff);
 
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -133,7 +137,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
         for (int i = 0; i < kEncRingStages; ++i) { mbar_init(&r_full[i], 1); mbar_init(&r_empty[i], 1); }
         mbar_init(q_done, 1); mbar_init(mg_done, 1); mbar_init(&h_done[0], 1); mbar_init(&h_done[1], 1);
         mbar_init(out_done, 1); mbar_init(g4_done, 1); mbar_init(g3m_done, 1);
-        mbar_init(qp_ready, 16); mbar_init(m_ready, 16); mbar_init(&hid_ready[0], 16); mbar_init(&hid_ready[1], 16);
+        for (int i = 0; i < 4; ++i) { mbar_init(&qp_ready[i], 8); mbar_init(&m_ready[i], 8); mbar_init(&hid_ready[i], 8); mbar_init(&hid_ready[4 + i], 8); }
         mbar_init(e4_done, 16);
         mbar_init(xr_full, 1);
         mbar_init(x0_done, 1);
@@ -182,14 +186,14 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     tma_load_3d_2sm(act + c * kEncChunk + 16384, &maps.x, &x_full[c], c * 64, m0, 1);
                     if (!(first && c < 3)) ring_load(&maps.wq, c * 64, wrow);
                 }
-                for (int c = 0; c < 4; ++c) ring_load(&maps.g, c * 64, seg * 256 + wrow);
+                for (int i = 0; i < 4; ++i) ring_load(&maps.g, chunk_order(i) * 64, seg * 256 + wrow);
                 for (int j = 0; j < 2; ++j) {
                     for (int c = 0; c < 4; ++c) {
                         if (j == 1) ring_load(&maps.x, c * 64, m0);   // chunk 0's x part runs while x is still resident in act
                         ring_load(&maps.w0, c * 64, j * 256 + wrow);
                     }
-                    for (int c = 0; c < 4; ++c) ring_load(&maps.w0, 256 + c * 64, j * 256 + wrow);
-                    for (int c = 0; c < 4; ++c) ring_load(&maps.w2, j * 256 + c * 64, wrow);
+                    for (int i = 0; i < 4; ++i) ring_load(&maps.w0, 256 + chunk_order(i) * 64, j * 256 + wrow);
+                    for (int i = 0; i < 4; ++i) ring_load(&maps.w2, j * 256 + chunk_order(i) * 64, wrow);
                 }
                 if (tma_e4) {
                     // the residual: this CTA's x rows once more (L2), into act as soon as mlp.0 is done reading m from it; the last
@@ -255,11 +259,12 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 if (first) enc_stamp(p, 4);
                 // ---- GEMM2: acc_mg (R1) = (Q*Z)[TMEM R0] . G^T   (R1 = acc_out of the previous tile until its last epilogue has read it)
                 if (!first) mbar_wait(e4_done, tp ^ 1u);
-                mbar_wait(qp_ready, tp);
-                tc_fence_after();
-                for (int c = 0; c < 4; ++c) {
+                for (int i = 0; i < 4; ++i) {
+                    const int c = chunk_order(i);
+                    mbar_wait(&qp_ready[c], tp);
+                    tc_fence_after();
                     const uint32_t b = ring_wait();
-                    mma_ts(R1, R0, c, b, c == 0);
+                    mma_ts(R1, R0, c, b, i == 0);
                     ring_release(b);
                 }
                 umma_commit_2sm(mg_done);
@@ -274,8 +279,6 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                 }
                 umma_commit_2sm(x0_done);
                 // ---- mlp: two 256-wide chunks of the hidden layer
-                mbar_wait(m_ready, tp);
-                tc_fence_after();
                 for (int j = 0; j < 2; ++j) {
                     if (j == 1) {
                         mbar_wait(g4_done, tp);                                  // relu(hid chunk 0) in R0 is no longer being read
@@ -288,18 +291,21 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                             ring_release(b);
                         }
                     }
-                    for (int c = 0; c < 4; ++c) {                                // m part (m resident in act)
+                    for (int i = 0; i < 4; ++i) {                                // m part (m resident in act, chunk by chunk as LayerNorm1 writes it)
+                        const int c = chunk_order(i);
+                        if (j == 0) { mbar_wait(&m_ready[c], tp); tc_fence_after(); }
                         const uint32_t b = ring_wait();
                         mma_ss(R0, act_a + c * kEncChunk, b, false);
                         ring_release(b);
                     }
                     if (j == 1) umma_commit_2sm(g3m_done);                       // act is free for the next tile's x
                     umma_commit_2sm(&h_done[j]);
-                    mbar_wait(&hid_ready[j], tp);
-                    tc_fence_after();
-                    for (int c = 0; c < 4; ++c) {                                // mlp.2 partial: acc_out (R1) += relu(hid_j)[TMEM R0] . W2_j^T
+                    for (int i = 0; i < 4; ++i) {                                // mlp.2 partial: acc_out (R1) += relu(hid_j)[TMEM R0] . W2_j^T
+                        const int c = chunk_order(i);
+                        mbar_wait(&hid_ready[4 * j + c], tp);
+                        tc_fence_after();
                         const uint32_t b = ring_wait();
-                        mma_ts(R1, R0, c, b, j == 0 && c == 0);
+                        mma_ts(R1, R0, c, b, j == 0 && i == 0);
                         ring_release(b);
                     }
                     if (j == 0) umma_commit_2sm(g4_done);
@@ -352,12 +358,14 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     uint32_t pk[32];
                     pack_block_hl(v, pk);
                     tmem_st32(tw + R0 + cb + 32 * b, pk);
+                    if (b & 1) {   // one 64-column K chunk of the merge GEMM is complete for this warp's rows
+                        tmem_st_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(&qp_ready[2 * half + (b >> 1)], 0);
+                    }
                 }
             }
-            tmem_st_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(qp_ready, 0);
             if (stamp) enc_stamp(p, 6);
             // ---- E2: LayerNorm1(acc_mg) -> m, written to act as the (hi, lo) A operand of mlp.0's second half
             mbar_wait(mg_done, tp);
@@ -400,12 +408,14 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                     const int phys = ((((col & 63) >> 3)) ^ (r & 7)) << 4;   // 128-byte swizzle: 16-byte unit index XOR (row mod 8)
                     *reinterpret_cast<uint4*>(chunk + phys) = uh;
                     *reinterpret_cast<uint4*>(chunk + 16384 + phys) = ul;
+                    if ((j8 & 7) == 7) {   // one 64-column chunk of m is complete for this warp's rows
+                        fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_remote(&m_ready[2 * half + (j8 >> 3)], 0);
+                    }
                 }
             }
-            fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_remote(m_ready, 0);
             if (stamp) enc_stamp(p, 8);
             // ---- E3: relu(hid chunk) packed in place as the A operand of mlp.2
 #pragma unroll 1
@@ -426,12 +436,14 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
                         uint32_t pk[32];
                         pack_block_hl(v, pk);
                         tmem_st32(tw + R0 + cb + 32 * b, pk);
+                        if (b & 1) {
+                            tmem_st_wait();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive_remote(&hid_ready[4 * j + 2 * half + (b >> 1)], 0);
+                        }
                     }
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_remote(&hid_ready[j], 0);
                 if (stamp && j == 1) enc_stamp(p, 10);
             }
             // ---- E4: x + LayerNorm2(acc_out) -> HBM
