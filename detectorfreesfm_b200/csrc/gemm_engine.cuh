@@ -1015,30 +1015,10 @@ struct KvEpi {
     static constexpr bool kHasState = true;
     static constexpr bool kSeparateCorr = false;
     static constexpr int kEpiStageBytes = 4096;
-    // The 32 x 32 outer-product sum of a head over the warp pair's 32 staged rows is a small matrix product D[d][v] += K'^T[d][s] V[s][v]
-    // (M = d, N = v, K = the rows): it runs on the tensor cores with warp-level mma.sync m16n8k8 (tf32 operands split hi + lo, three
-    // products, fp32 accumulate -- ~2^-21 relative), each warp of the pair taking all 32 d and 16 of the v: 12 MMAs and 12 conflict-free
-    // scalar shared loads per 8 rows (Ksum: plain adds of the loaded K' values, reduced over the lane group when the state is flushed).  The SIMT version it replaces (kKvMma = false:
-    // 4 d x 4 v register tiles, two 128-bit loads + 20 FMAs per row) was bound by its 8192 FMAs per token: ~9 us per tile next to 3.2 us
-    // of projection MMAs (profiles/r02_timeline_fused.log).
-    // Index maps chosen so that the fragment loads hit 32 distinct banks of the swizzled staging rows (LinEpi::stage_rows):
-    //   MMA row r16 = g + 8f of M tile mi  <->  d = 8 mi + 4 f + 16 (g >> 2) + (g & 3)
-    //   MMA column j of N tile ni          <->  v = 16 (j >> 2) + 8 half + 4 ni + (j & 3)            (g = lane >> 2, t = lane & 3)
-    static constexpr bool kKvMma = true;
-    static __device__ __forceinline__ int d_of(int mi, int f, int g) { return 8 * mi + 4 * f + 16 * (g >> 2) + (g & 3); }
-    static __device__ __forceinline__ int v_of(int half, int ni, int j) { return 16 * (j >> 2) + 8 * half + 4 * ni + (j & 3); }
-    static __device__ __forceinline__ float stg_ld(const uint8_t* stg, int row, int col) {
-        return *reinterpret_cast<const float*>(stg + row * 128 + ((((col >> 2) ^ (row & 7))) << 4) + ((col & 3) << 2));
-    }
-    static __device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-        lo = __float_as_uint(x - __uint_as_float(hi));   // the tensor core drops the low 13 bits: 2^-22 of x
-    }
-    static __device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-        asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-                     : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                     : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-    }
+    // Register tile of a thread: 4 d x 4 v of each head's 32 x 32 outer-product sum (lane = (dq, vq): d = 4*dq + i, v = 16*half + 4*vq + j).
+    // Per staged row a thread then loads ONE 16-byte K unit and ONE 16-byte V unit for 16 FMAs -- a 128-bit shared load costs four
+    // wavefronts per warp whatever the addresses, so the (1 d x 16 v) tile of the first version (five loads per 16 FMAs, 17 wavefronts
+    // per row) made the epilogue LSU-bound at ~15 us per tile (profiles/r02_timeline_fused.log); this layout needs 8.
     struct State {
         float acc[4][16];
         float ks[4][4];
@@ -1068,37 +1048,12 @@ struct KvEpi {
             if (quad == q) {
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
-                    if (kKvMma) {
-                        // acc[h][(mi*2 + ni)*4 + e]: MMA accumulator register e of tile (mi, ni); ks[h][mi*2 + f]: Ksum of row g + 8f of M tile mi
 #pragma unroll
-                        for (int mi = 0; mi < 2; ++mi) {
+                    for (int i = 0; i < 4; ++i) {
+                        float* r = red + (h * 32 + dq * 4 + i) * 33;
 #pragma unroll
-                            for (int f = 0; f < 2; ++f) {
-                                float* r = red + (h * 32 + d_of(mi, f, dq)) * 33;
-#pragma unroll
-                                for (int ni = 0; ni < 2; ++ni) {
-#pragma unroll
-                                    for (int e = 0; e < 2; ++e) {
-                                        const int v = v_of(half, ni, 2 * vq + e);
-                                        r[v] = (q == 0 ? 0.f : r[v]) + st.acc[h][(mi * 2 + ni) * 4 + 2 * f + e];
-                                    }
-                                }
-                                if (half == 0) {   // the four lanes of a group hold the partial sums of different rows
-                                    float ksum = st.ks[h][mi * 2 + f];
-                                    ksum += __shfl_xor_sync(0xffffffffu, ksum, 1);
-                                    ksum += __shfl_xor_sync(0xffffffffu, ksum, 2);
-                                    if (vq == 0) r[32] = (q == 0 ? 0.f : r[32]) + ksum;
-                                }
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            float* r = red + (h * 32 + dq * 4 + i) * 33;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) r[half * 16 + vq * 4 + j] = (q == 0 ? 0.f : r[half * 16 + vq * 4 + j]) + st.acc[h][4 * i + j];
-                            if (half == 0 && vq == 0) r[32] = (q == 0 ? 0.f : r[32]) + st.ks[h][i];
-                        }
+                        for (int j = 0; j < 4; ++j) r[half * 16 + vq * 4 + j] = (q == 0 ? 0.f : r[half * 16 + vq * 4 + j]) + st.acc[h][4 * i + j];
+                        if (half == 0 && vq == 0) r[32] = (q == 0 ? 0.f : r[32]) + st.ks[h][i];
                     }
                 }
             }
@@ -1140,51 +1095,6 @@ struct KvEpi {
             }
             LinEpi::stage_rows(ctx.stg, lane, v);
             named_bar_sync(ctx.bar_id, 64);
-            if (kKvMma) {
-                const int g = lane >> 2, t = lane & 3;
-                float c[4][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) c[i][e] = st.acc[h][4 * i + e];
-                }
-                float k0 = st.ks[h][0], k1 = st.ks[h][1], k2 = st.ks[h][2], k3 = st.ks[h][3];   // Ksum partials of d_of(mi, f, g) over this lane's rows
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {   // 8 staged rows per step
-                    const int r0 = 8 * kk + t, r1 = r0 + 4;
-                    uint32_t bh[2][2], bl[2][2];
-#pragma unroll
-                    for (int ni = 0; ni < 2; ++ni) {
-                        tf32_split(stg_ld(vst, r0, v_of(half, ni, g)), bh[ni][0], bl[ni][0]);
-                        tf32_split(stg_ld(vst, r1, v_of(half, ni, g)), bh[ni][1], bl[ni][1]);
-                    }
-#pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) {   // one M tile at a time: 8 fragment registers live instead of 16
-                        const float x0 = stg_ld(kst, r0, d_of(mi, 0, g)), x1 = stg_ld(kst, r0, d_of(mi, 1, g));
-                        const float x2 = stg_ld(kst, r1, d_of(mi, 0, g)), x3 = stg_ld(kst, r1, d_of(mi, 1, g));
-                        if (mi == 0) { k0 += x0 + x2; k1 += x1 + x3; } else { k2 += x0 + x2; k3 += x1 + x3; }
-                        uint32_t ah[4], al[4];
-                        tf32_split(x0, ah[0], al[0]);
-                        tf32_split(x1, ah[1], al[1]);
-                        tf32_split(x2, ah[2], al[2]);
-                        tf32_split(x3, ah[3], al[3]);
-#pragma unroll
-                        for (int ni = 0; ni < 2; ++ni) {
-                            mma_tf32(c[mi * 2 + ni], ah, bh[ni][0], bh[ni][1]);
-                            mma_tf32(c[mi * 2 + ni], ah, bl[ni][0], bl[ni][1]);
-                            mma_tf32(c[mi * 2 + ni], al, bh[ni][0], bh[ni][1]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) st.acc[h][4 * i + e] = c[i][e];
-                }
-                st.ks[h][0] = k0; st.ks[h][1] = k1; st.ks[h][2] = k2; st.ks[h][3] = k3;
-                named_bar_sync(ctx.bar_id, 64);  // both warps are done reading the staged blocks
-                continue;
-            }
             float a[16], k0 = st.ks[h][0], k1 = st.ks[h][1], k2 = st.ks[h][2], k3 = st.ks[h][3];
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = st.acc[h][j];
