@@ -1019,6 +1019,9 @@ struct KvEpi {
     // Per staged row a thread then loads ONE 16-byte K unit and ONE 16-byte V unit for 16 FMAs -- a 128-bit shared load costs four
     // wavefronts per warp whatever the addresses, so the (1 d x 16 v) tile of the first version (five loads per 16 FMAs, 17 wavefronts
     // per row) made the epilogue LSU-bound at ~15 us per tile (profiles/r02_timeline_fused.log); this layout needs 8.
+    // Tried and measured slower: the same reduction as a warp-level tensor-core product (mma.sync m16n8k8 tf32, split hi + lo, conflict-free
+    // fragment loads; commit 'KvEpi: the K^T V state reduction on warp-level tf32 tensor-core MMAs', parity green) -- 16 us per tile instead
+    // of 8.9: the legacy HMMA.1688.TF32 path of sm_100 issues at ~20 clocks per instruction per SM here, far below the FFMA rate it replaces.
     struct State {
         float acc[4][16];
         float ks[4][4];
