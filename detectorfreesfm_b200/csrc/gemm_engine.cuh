@@ -226,12 +226,6 @@ struct Gemm2Cfg {
     static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256 && (BN / 2) % 8 == 0, "invalid UMMA N for a CTA pair");
 };
 
-__device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, int bo_mode) {
-    uint64_t d = make_smem_desc_sw128(smem_addr);
-    if (bo_mode) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
-    return d;
-}
-
 // Tile order of a cluster.  Static: tile = cluster + k * clusters with min(tiles, SM pairs) clusters in the grid.  Stealing: the grid has
 // ONE cluster per tile; while a cluster works on a tile its producer asks the hardware to cancel a cluster of the grid that has not been
 // launched yet (cluster launch control) and the whole cluster takes that tile next, until nothing is left to cancel.  Clusters that start
@@ -389,21 +383,32 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
                     const uint32_t a_hi = smem_u32(smem + s * Cfg::kStageBytes);
                     const uint32_t b_hi = a_hi + Cfg::kPlanes * Cfg::kABytes;
                     const int nk = (c == core.kchunks - 1) ? core.k16_last : 4;
+                    // One descriptor per operand plane and stage; every MMA's descriptors are that plus a small constant in the 16-byte
+                    // address field (K step k: +32 B; tap i of a slab: +i rows = +128 B inside the swizzle atom; lo plane; tap's weight
+                    // tile).  The issuing thread is on the critical path of a 128-column tile (64 clocks per MMA at the peak rate): built
+                    // from scratch per MMA the descriptors cost ~17 dependent uniform-datapath instructions each.
+                    const uint64_t da0 = make_smem_desc_sw128(a_hi), db0 = make_smem_desc_sw128(b_hi);
+                    auto issue = [&](int i, int k) {
+                        const uint64_t bo = (G > 1 && core.bo_mode) ? (static_cast<uint64_t>(i) << 49) : 0;  // debug hook only (dfsfm_debug_gemm2)
+                        const uint64_t da = (da0 + static_cast<uint64_t>(i * 8 + k * 2)) | bo;
+                        const uint64_t db = db0 + static_cast<uint64_t>(i * (Cfg::kBTapBytes >> 4) + k * 2);
+                        umma_f16_2sm(tmem_acc, da, db, idesc, acc);
+                        if (kSplit) {
+                            umma_f16_2sm(tmem_corr, da, db + (Cfg::kBBytes >> 4), idesc, Epi::kSeparateCorr ? acc : 1u);
+                            umma_f16_2sm(tmem_corr, da + (Cfg::kABytes >> 4), db, idesc, 1);
+                        }
+                        acc = 1;
+                    };
+                    if (nk == 4) {
 #pragma unroll
-                    for (int i = 0; i < G; ++i) {
-                        for (int k = 0; k < nk; ++k) {
-                            // tap i of the group reads the slab advanced by i rows (i * 128 bytes inside the swizzle atom)
-                            const uint64_t da = G == 1 ? make_smem_desc_sw128(a_hi + k * 32) : make_smem_desc_sw128_bo(a_hi + i * 128 + k * 32, core.bo_mode);
-                            const uint64_t db = make_smem_desc_sw128(b_hi + i * Cfg::kBTapBytes + k * 32);
-                            umma_f16_2sm(tmem_acc, da, db, idesc, acc);
-                            if (kSplit) {
-                                const uint64_t dal = G == 1 ? make_smem_desc_sw128(a_hi + Cfg::kABytes + k * 32)
-                                                            : make_smem_desc_sw128_bo(a_hi + Cfg::kABytes + i * 128 + k * 32, core.bo_mode);
-                                const uint64_t dbl = make_smem_desc_sw128(b_hi + Cfg::kBBytes + i * Cfg::kBTapBytes + k * 32);
-                                umma_f16_2sm(tmem_corr, da, dbl, idesc, Epi::kSeparateCorr ? acc : 1u);
-                                umma_f16_2sm(tmem_corr, dal, db, idesc, 1);
-                            }
-                            acc = 1;
+                        for (int i = 0; i < G; ++i) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) issue(i, k);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < G; ++i) {
+                            for (int k = 0; k < nk; ++k) issue(i, k);
                         }
                     }
                     umma_commit_2sm(&empty_bar[s]);
