@@ -169,7 +169,7 @@ static ParityBuf parity_alloc(long long rows, int C) {
     p.C = C;
     const size_t bytes = static_cast<size_t>(8) * rows * C * sizeof(__half);
     DFSFM_CUDA(cudaMalloc(&p.base, bytes));
-    DFSFM_CUDA(cudaMemset(p.base, 0, bytes));
+    zero_device_sync(p.base, 0, bytes);
     return p;
 }
 
@@ -422,7 +422,7 @@ void CoarseEngine::ensure_tok(int n) {
     DFSFM_CUDA(cudaMalloc(&tok_.ksum, 512 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kvp_part, static_cast<size_t>(4) * sm_count() * kKvPartFloats * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kvp_flags, static_cast<size_t>(4) * sm_count() * sizeof(unsigned)));
-    DFSFM_CUDA(cudaMemset(tok_.kvp_flags, 0, static_cast<size_t>(4) * sm_count() * sizeof(unsigned)));
+    zero_device_sync(tok_.kvp_flags, 0, static_cast<size_t>(4) * sm_count() * sizeof(unsigned));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_part, static_cast<size_t>(2) * tok_.kv_chunks * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.kv_state, static_cast<size_t>(2) * 256 * 33 * sizeof(float)));
     DFSFM_CUDA(cudaMalloc(&tok_.seg_dev, 8 * sizeof(Seg)));

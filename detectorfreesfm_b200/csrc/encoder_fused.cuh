@@ -226,22 +226,26 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
             };
             auto ring_release = [&](uint32_t stage_addr) { umma_commit_2sm(&r_empty[(stage_addr - ring_a) / kEncChunk]); };
             // one 64-wide K chunk, both operands in shared memory: 4 K steps x (hi*hi, hi*lo, lo*hi)
+            // (descriptors: one per operand and chunk, plus a constant in the 16-byte address field per K step / lo plane)
             auto mma_ss = [&](uint32_t d, uint32_t a, uint32_t b, bool fresh) {
+                const uint64_t da0 = make_smem_desc_sw128(a), db0 = make_smem_desc_sw128(b);
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t da = make_smem_desc_sw128(a + k * 32), db = make_smem_desc_sw128(b + k * 32);
-                    const uint64_t dal = make_smem_desc_sw128(a + 16384 + k * 32), dbl = make_smem_desc_sw128(b + 16384 + k * 32);
+                    const uint64_t da = da0 + 2u * k, db = db0 + 2u * k;
                     umma_f16_2sm(tmem_base + d, da, db, idesc, (fresh && k == 0) ? 0u : 1u);
-                    umma_f16_2sm(tmem_base + d, da, dbl, idesc, 1u);
-                    umma_f16_2sm(tmem_base + d, dal, db, idesc, 1u);
+                    umma_f16_2sm(tmem_base + d, da, db + (16384 >> 4), idesc, 1u);
+                    umma_f16_2sm(tmem_base + d, da + (16384 >> 4), db, idesc, 1u);
                 }
             };
             // the same with the A operand in tensor memory: chunk c of a 256-wide packed activation at TMEM columns a0 ..
             auto mma_ts = [&](uint32_t d, uint32_t a0, int c, uint32_t b, bool fresh) {
+                const uint64_t db0 = make_smem_desc_sw128(b);
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const uint32_t blk = tmem_base + a0 + 32u * static_cast<uint32_t>(2 * c + (k >> 1)) + 8u * static_cast<uint32_t>(k & 1);
-                    const uint64_t db = make_smem_desc_sw128(b + k * 32), dbl = make_smem_desc_sw128(b + 16384 + k * 32);
+                    const uint64_t db = db0 + 2u * k;
                     umma_f16_2sm_ts(tmem_base + d, blk, db, idesc, (fresh && k == 0) ? 0u : 1u);
-                    umma_f16_2sm_ts(tmem_base + d, blk, dbl, idesc, 1u);
+                    umma_f16_2sm_ts(tmem_base + d, blk, db + (16384 >> 4), idesc, 1u);
                     umma_f16_2sm_ts(tmem_base + d, blk + 16u, db, idesc, 1u);
                 }
             };

@@ -193,6 +193,7 @@ class ParamStore {
             if (it != mats_.end()) { hl_free(it->second); mats_.erase(it); }
             HL b = hl_alloc(rows, static_cast<int>(cols));
             DFSFM_CUDA(cudaMemcpy(b.hi, tmp.data(), tmp.size() * sizeof(__half), cudaMemcpyHostToDevice));
+            DFSFM_CUDA(cudaStreamSynchronize(cudaStreamLegacy));  // pageable source: the DMA may still be in flight, and non-blocking streams do not wait for it
             mats_[name] = b;
         } else {
             auto it = vecs_.find(name);
@@ -200,6 +201,7 @@ class ParamStore {
             float* d = nullptr;
             DFSFM_CUDA(cudaMalloc(&d, static_cast<size_t>(n) * sizeof(float)));
             DFSFM_CUDA(cudaMemcpy(d, host, static_cast<size_t>(n) * sizeof(float), cudaMemcpyHostToDevice));
+            DFSFM_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
             vecs_[name] = d;
         }
     }

@@ -44,12 +44,18 @@ struct HL {
     size_t bytes() const { return static_cast<size_t>(rows) * C * 2 * sizeof(__half); }
 };
 
+// Allocation-time zero fill (halo cells, flags): cudaMemset runs in the legacy default stream, which does NOT order against the non-blocking
+// streams the engines are driven on (a pair worker's side stream: its first kernels could read a halo before the fill had run) -- wait for it.
+inline void zero_device_sync(void* p, int value, size_t bytes) {
+    DFSFM_CUDA(cudaMemset(p, value, bytes));
+    DFSFM_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+}
 inline HL hl_alloc(long long rows, int C) {
     HL b;
     b.rows = rows;
     b.C = C;
     DFSFM_CUDA(cudaMalloc(&b.hi, b.bytes()));
-    DFSFM_CUDA(cudaMemset(b.hi, 0, b.bytes()));
+    zero_device_sync(b.hi, 0, b.bytes());
     return b;
 }
 inline void hl_free(HL& b) {

@@ -120,12 +120,13 @@ mlp128_fused_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p, con
                     mbar_wait(&w_full[ws], wphase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(act + c * 32768), b_hi = smem_u32(ring + ws * kMlpRingStage);
+                    const uint64_t da0 = make_smem_desc_sw128(a_hi), db0 = make_smem_desc_sw128(b_hi);   // + constants per K step / lo plane
+#pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(a_hi + k * 32), db = make_smem_desc_sw128(b_hi + k * 32);
-                        const uint64_t dal = make_smem_desc_sw128(a_hi + 16384 + k * 32), dbl = make_smem_desc_sw128(b_hi + 16384 + k * 32);
+                        const uint64_t da = da0 + 2u * k, db = db0 + 2u * k;
                         umma_f16_2sm(tmem_base + kAcc2, da, db, idesc2, acc);
-                        umma_f16_2sm(tmem_base + kAcc2, da, dbl, idesc2, 1);
-                        umma_f16_2sm(tmem_base + kAcc2, dal, db, idesc2, 1);
+                        umma_f16_2sm(tmem_base + kAcc2, da, db + (16384 >> 4), idesc2, 1);
+                        umma_f16_2sm(tmem_base + kAcc2, da + (16384 >> 4), db, idesc2, 1);
                         acc = 1;
                     }
                     umma_commit_2sm(&w_empty[ws]);
@@ -141,12 +142,13 @@ mlp128_fused_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p, con
                     mbar_wait(&w_full[ws], wphase);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(act + c * 32768), b_hi = smem_u32(ring + ws * kMlpRingStage);
+                    const uint64_t da0 = make_smem_desc_sw128(a_hi), db0 = make_smem_desc_sw128(b_hi);
+#pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = make_smem_desc_sw128(a_hi + k * 32), db = make_smem_desc_sw128(b_hi + k * 32);
-                        const uint64_t dal = make_smem_desc_sw128(a_hi + 16384 + k * 32), dbl = make_smem_desc_sw128(b_hi + 8192 + k * 32);
+                        const uint64_t da = da0 + 2u * k, db = db0 + 2u * k;
                         umma_f16_2sm(tmem_base + kAcc3, da, db, idesc3, acc);
-                        umma_f16_2sm(tmem_base + kAcc3, da, dbl, idesc3, 1);
-                        umma_f16_2sm(tmem_base + kAcc3, dal, db, idesc3, 1);
+                        umma_f16_2sm(tmem_base + kAcc3, da, db + (8192 >> 4), idesc3, 1);
+                        umma_f16_2sm(tmem_base + kAcc3, da + (16384 >> 4), db, idesc3, 1);
                         acc = 1;
                     }
                     umma_commit_2sm(&w_empty[ws]);

@@ -29,7 +29,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         cap = n + n / 8;
         DFSFM_CUDA(cudaMalloc(&p, cap * sizeof(T)));
-        DFSFM_CUDA(cudaMemset(p, 0, cap * sizeof(T)));
+        zero_device_sync(p, 0, cap * sizeof(T));
     }
     ~DevBuf() { if (p) cudaFree(p); }
 };
