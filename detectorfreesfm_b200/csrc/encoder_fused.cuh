@@ -158,7 +158,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
 
     if (warp == 0) {
         // ===================================================================================== TMA producer (one thread per CTA)
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t it = 0;   // ring items issued so far
             uint32_t tp = 0;   // parity of the per-tile barriers
             bool first = true;
@@ -212,7 +212,7 @@ enc256_fused_kernel(const __grid_constant__ EncMaps maps, const EncParams p, con
         __syncwarp();
     } else if (warp == 1) {
         // ===================================================================================== MMA issuer (leader CTA, one thread)
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(256, 256);
             uint32_t it = 0, tp = 0;
             bool first = true;

@@ -332,7 +332,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
     ts.steal = steal != 0;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int s = 0;
             uint32_t phase = 0;
             for (int tile = ts.first(); tile >= 0; tile = ts.next()) {
@@ -363,7 +363,7 @@ gemm_tc2_kernel(const __grid_constant__ TmapPack maps, const GemmCore core, cons
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(2 * kBM, BN);
             int s = 0;
             uint32_t phase = 0;

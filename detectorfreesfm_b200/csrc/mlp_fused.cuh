@@ -74,7 +74,7 @@ mlp128_fused_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p, con
     constexpr uint32_t kAcc2 = 0, kAcc3 = 256;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int ws = 0;
             uint32_t wphase = 0, tphase = 0;
             bool first = true;
@@ -106,7 +106,7 @@ mlp128_fused_kernel(const __grid_constant__ MlpMaps maps, const MlpParams p, con
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc2 = make_idesc_f16(256, 256);
             constexpr uint32_t idesc3 = make_idesc_f16(256, 128);
             int ws = 0;
