@@ -71,7 +71,7 @@ def match_workers(all_subset_ids, image_lists, covis_pairs_out, cfgs, matchers, 
     host thread driving ``match_worker`` with its OWN matcher (own engine handle and workspaces) on its OWN CUDA stream of the current
     device; the threads spend their time inside the C ABI and CUDA calls (GIL released), so the pairs of different workers overlap on the
     GPU.  At 832x832 a single pair leaves ~40 % of the SMs idle in the transformer (43 / 86 tiles for 74 CTA pairs, DESIGN.md section
-    6); two workers measured +18 % pairs/s, three +24 %.  (Ordering the workers' backbone phases with events -- one worker's backbone
+    6); two workers measured +15-20 % pairs/s, three +27 %.  (Ordering the workers' backbone phases with events -- one worker's backbone
     always beside another's transformer -- was tried and measured WORSE, 204-243 vs 229-255 pairs/s: profiles/r02_worker_pool.txt.)
 
     ``matchers``: one per subset (e.g. ``[build_model(cfg) for _ in range(n)]``).  ``datasets``: optional, one per subset.
