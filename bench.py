@@ -320,10 +320,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "3")),
+    ap.add_argument("--workers-per-gpu", type=int, default=int(os.environ.get("DFSFM_BENCH_WORKERS", "1")),
                     help="concurrent pair workers per GPU, each with its own matcher (engine handle + workspaces) and CUDA stream -- the reference's "
-                         "built-in config shares a GPU between Ray workers the same way (n_gpus_per_worker: 0.5, src/coarse_match/coarse_match.py:53); "
-                         "three measured the most stable run to run (profiles/r02_worker_pool.txt)")
+                         "built-in config shares a GPU between Ray workers the same way (n_gpus_per_worker: 0.5, src/coarse_match/coarse_match.py:53). "
+                         "Default 1: three workers measured +27 %% pairs/s (profiles/r02_worker_pool.txt) but a bench invocation with three "
+                         "workers at 832x832 hung intermittently on the GPU (profiles/r02_pool_hang.txt, unresolved), so the pool is opt-in")
     ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"],
                     help="c2 (default): the headline line, one demo scene per rank; c4: IMC-style full pair graph (5050 pairs of 101 images) sharded "
                          "over the ranks, strong scaling; c5: Bridge-scale refinement, --c5-chunks chunks of 2000 tracks sharded over the ranks")

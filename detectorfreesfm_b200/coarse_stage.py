@@ -74,6 +74,10 @@ def match_workers(all_subset_ids, image_lists, covis_pairs_out, cfgs, matchers, 
     6); two workers measured +15-20 % pairs/s, three +27 %.  (Ordering the workers' backbone phases with events -- one worker's backbone
     always beside another's transformer -- was tried and measured WORSE, 204-243 vs 229-255 pairs/s: profiles/r02_worker_pool.txt.)
 
+    OPEN ISSUE: with three workers at 832x832 about one bench invocation in five stopped making progress on the device
+    (profiles/r02_pool_hang.txt; never with one stream, never at small sizes, not reproduced with two workers) -- the pool is an opt-in
+    until that is understood; bench.py defaults to one worker.
+
     ``matchers``: one per subset (e.g. ``[build_model(cfg) for _ in range(n)]``).  ``datasets``: optional, one per subset.
     Results are identical to one worker's (every pair is computed independently); key collisions resolve like ``dict(ChainMap(*results))``.
     """
