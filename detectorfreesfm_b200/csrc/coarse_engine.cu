@@ -267,36 +267,32 @@ void CoarseEngine::features(const float* img, int H, int W, const float* pe, flo
     { const HL in[1] = {w.b2}; conv<128>(in, 1, c, "l1.0.c2", epi_flat(w.g2, 128, w.c2, true, &w.a2), st); }
     { const HL in[1] = {w.c2}; conv<128>(in, 1, c, "l1.1.c1", epi_flat(w.g2, 128, w.b2, true, nullptr), st); }
     { const HL in[1] = {w.b2}; conv<128>(in, 1, c, "l1.1.c2", epi_parity(w.g2, 128, w.p1, true, &w.c2), st); }
-    // Column tiles: the 208- and 256-channel layers run as TWO column tiles of 112 / 128 per 256-row tile.  One wide tile needs main +
-    // correction accumulators of 2 x 256 TMEM columns = all 512: a single accumulator set, so its epilogue (11 us at 208 columns) ran
-    // exposed after every tile's MMAs; at <= 128 columns two sets fit, the epilogue hides under the next tile's MMAs, and the 3x3
-    // stride-1 launches get the activation slab (one load per kernel row instead of three).
     // layer2 (stride 2, 196 -> 208 padded channels) -- the 1x1 stride-2 downsample rides as a 10th tap of conv2
     c.M = static_cast<int>(w.g4.rows);
     set_k(c, 128);
     conv_taps_s2(c, w.g4.Wp);
     { const HL in[4] = {w.p1.plane(0), w.p1.plane(1), w.p1.plane(2), w.p1.plane(3)};
-      conv<112>(in, 4, c, "l2.0.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
+      conv<208>(in, 4, c, "l2.0.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
     set_k(c, 208);
     conv_taps_s1(c, 3, w.g4.Wp);
     c.num_taps = 10; c.tap_map[9] = 1; c.tap_shift[9] = 0;
-    { const HL in[2] = {w.a4, w.p1.plane(0)}; conv<112>(in, 2, c, "l2.0.c2", epi_flat(w.g4, 208, w.b4, true, nullptr), st); }
+    { const HL in[2] = {w.a4, w.p1.plane(0)}; conv<208>(in, 2, c, "l2.0.c2", epi_flat(w.g4, 208, w.b4, true, nullptr), st); }
     conv_taps_s1(c, 3, w.g4.Wp);
-    { const HL in[1] = {w.b4}; conv<112>(in, 1, c, "l2.1.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
-    { const HL in[1] = {w.a4}; conv<112>(in, 1, c, "l2.1.c2", epi_parity(w.g4, 208, w.p2, true, &w.b4), st); }
+    { const HL in[1] = {w.b4}; conv<208>(in, 1, c, "l2.1.c1", epi_flat(w.g4, 208, w.a4, true, nullptr), st); }
+    { const HL in[1] = {w.a4}; conv<208>(in, 1, c, "l2.1.c2", epi_parity(w.g4, 208, w.p2, true, &w.b4), st); }
     // layer3 (stride 2, 256 ch)
     c.M = static_cast<int>(w.g8.rows);
     set_k(c, 208);
     conv_taps_s2(c, w.g8.Wp);
     { const HL in[4] = {w.p2.plane(0), w.p2.plane(1), w.p2.plane(2), w.p2.plane(3)};
-      conv<128>(in, 4, c, "l3.0.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
+      conv<256>(in, 4, c, "l3.0.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
     set_k(c, 256);
     conv_taps_s1(c, 3, w.g8.Wp);
     c.num_taps = 10; c.tap_map[9] = 1; c.tap_shift[9] = 0;
-    { const HL in[2] = {w.a8, w.p2.plane(0)}; conv<128>(in, 2, c, "l3.0.c2", epi_flat(w.g8, 256, w.b8, true, nullptr), st); }
+    { const HL in[2] = {w.a8, w.p2.plane(0)}; conv<256>(in, 2, c, "l3.0.c2", epi_flat(w.g8, 256, w.b8, true, nullptr), st); }
     conv_taps_s1(c, 3, w.g8.Wp);
-    { const HL in[1] = {w.b8}; conv<128>(in, 1, c, "l3.1.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
-    { const HL in[1] = {w.a8}; conv<128>(in, 1, c, "l3.1.c2", epi_flat(w.g8, 256, w.c8, true, &w.b8), st); }
+    { const HL in[1] = {w.b8}; conv<256>(in, 1, c, "l3.1.c1", epi_flat(w.g8, 256, w.a8, true, nullptr), st); }
+    { const HL in[1] = {w.a8}; conv<256>(in, 1, c, "l3.1.c2", epi_flat(w.g8, 256, w.c8, true, &w.b8), st); }
     // layer3_outconv (1x1) + position encoding + flatten to tokens (resnet_fpn.py:108, loftr.py:58)
     conv_taps_s1(c, 1, w.g8.Wp);
     {
@@ -321,10 +317,10 @@ void CoarseEngine::features(const float* img, int H, int W, const float* pe, flo
             // OUT_DENSE and OUT_FLAT differ only in the row mapping, so the planes come from a second epilogue pass below.
         }
         const HL in[1] = {w.c8};
-        conv<128>(in, 1, c, "out3", e, st);
+        conv<256>(in, 1, c, "out3", e, st);
         if (feat_f) {
             ConvEpiParams e2 = epi_flat(w.g8, 256, w.x3o, false, nullptr);
-            conv<128>(in, 1, c, "out3", e2, st);
+            conv<256>(in, 1, c, "out3", e2, st);
             fine_branch(w, feat_f, st);
         }
     }
@@ -350,14 +346,14 @@ void CoarseEngine::fine_branch(FeatWs& w, float* feat_f, cudaStream_t st) {
         e.N = 256; e.g = w.g8.flat(); e.out_mode = OUT_UNPARITY; e.upy = k >> 1; e.upx = k & 1; e.ohp = w.g4.Hp; e.owp = w.g4.Wp;
         e.out_f32 = w.f4; e.out_f32_ld = 256;
         const HL in[1] = {w.p2.plane(k)};
-        conv<128>(in, 1, c, "fpn.l2o", e, st);
+        conv<256>(in, 1, c, "fpn.l2o", e, st);
     }
     up_add(w.x3o, w.g8, 256, w.f4, w.t4a);
     c.M = static_cast<int>(w.g4.rows);
     set_k(c, 256);
     conv_taps_s1(c, 3, w.g4.Wp);
-    { ConvEpiParams e = epi_flat(w.g4, 256, w.t4b, false, nullptr); e.relu = 2; const HL in[1] = {w.t4a}; conv<128>(in, 1, c, "fpn.l2o2a", e, st); }
-    { ConvEpiParams e = epi_flat(w.g4, 208, w.x2o, false, nullptr); const HL in[1] = {w.t4b}; conv<112>(in, 1, c, "fpn.l2o2b", e, st); }
+    { ConvEpiParams e = epi_flat(w.g4, 256, w.t4b, false, nullptr); e.relu = 2; const HL in[1] = {w.t4a}; conv<256>(in, 1, c, "fpn.l2o2a", e, st); }
+    { ConvEpiParams e = epi_flat(w.g4, 208, w.x2o, false, nullptr); const HL in[1] = {w.t4b}; conv<208>(in, 1, c, "fpn.l2o2b", e, st); }
     // x1_out = layer1_outconv(x1) [1x1 on the parity planes of x1] + up(x2_out)
     set_k(c, 128);
     conv_taps_s1(c, 1, w.g4.Wp);
@@ -367,13 +363,13 @@ void CoarseEngine::fine_branch(FeatWs& w, float* feat_f, cudaStream_t st) {
         e.N = 208; e.g = w.g4.flat(); e.out_mode = OUT_UNPARITY; e.upy = k >> 1; e.upx = k & 1; e.ohp = w.g2.Hp; e.owp = w.g2.Wp;
         e.out_f32 = w.f2; e.out_f32_ld = 208;
         const HL in[1] = {w.p1.plane(k)};
-        conv<112>(in, 1, c, "fpn.l1o", e, st);
+        conv<208>(in, 1, c, "fpn.l1o", e, st);
     }
     up_add(w.x2o, w.g4, 208, w.f2, w.t2a);
     c.M = static_cast<int>(w.g2.rows);
     set_k(c, 208);
     conv_taps_s1(c, 3, w.g2.Wp);
-    { ConvEpiParams e = epi_flat(w.g2, 208, w.t2b, false, nullptr); e.relu = 2; const HL in[1] = {w.t2a}; conv<112>(in, 1, c, "fpn.l1o2a", e, st); }
+    { ConvEpiParams e = epi_flat(w.g2, 208, w.t2b, false, nullptr); e.relu = 2; const HL in[1] = {w.t2a}; conv<208>(in, 1, c, "fpn.l1o2a", e, st); }
     {
         ConvEpiParams e;
         memset(&e, 0, sizeof(e));

@@ -570,9 +570,7 @@ struct ConvEpi {
             load_acc32<kCorr>(tmem_warp + c0, v);  // warp-collective: every lane executes it
             const int nb = n0 + c0;
             if (!valid || nb >= p.N) continue;
-            // columns to write in this chunk (a multiple of 8; may exceed 32): up to the tensor's width AND the tile's own width -- a
-            // 112-column tile loads accumulator columns 96..127, of which 112..127 belong to the next column tile
-            const int ncnt = (p.N - nb) < (BN - c0) ? (p.N - nb) : (BN - c0);
+            const int ncnt = p.N - nb;  // columns to write in this chunk (a multiple of 8; may exceed 32)
             if (p.bias) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {

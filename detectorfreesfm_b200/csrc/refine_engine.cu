@@ -335,9 +335,9 @@ void RefineEngine::chunk(int n_img, const float* const* images, const int32_t* H
     { ConvEpiParams e = epi(g18_, 128, true); set_out(e, c21_.b); conv<128>(p1_.b, g18_, P, 3, 64, "c21", e, st); }
     { ConvEpiParams e = epi(g18_, 128, true); set_out(e, c22_.b); conv<128>(c21_.b, g18_, P, 3, 128, "c22", e, st); }
     pool(c22_.b, g18_, p2_.b, g9_, 128);
-    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c31_.b); conv<128>(p2_.b, g9_, P, 3, 128, "c31", e, st); }
-    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c32_.b); conv<128>(c31_.b, g9_, P, 3, 256, "c32", e, st); }
-    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c33_.b); conv<128>(c32_.b, g9_, P, 3, 256, "c33", e, st); }
+    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c31_.b); conv<256>(p2_.b, g9_, P, 3, 128, "c31", e, st); }
+    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c32_.b); conv<256>(c31_.b, g9_, P, 3, 256, "c32", e, st); }
+    { ConvEpiParams e = epi(g9_, 256, true); set_out(e, c33_.b); conv<256>(c32_.b, g9_, P, 3, 256, "c33", e, st); }
     // adaptation layer 0 on relu1_2: 1x1 (+ReLU) only where the 5x5 needs it, then 5x5 + BN on the centre window
     {
         ConvEpiParams e = epi(g35_, 64, true);
