@@ -65,7 +65,7 @@ def test_coarse_matching_stage_matches_oracle_chain(tmp_path):
     assert n_total > 10
 
 
-@pytest.mark.timeout(300)   # the pool has an unresolved intermittent device hang at 832x832 with three workers (profiles/r02_pool_hang.txt);
+@pytest.mark.timeout(300, method="thread")   # the pool has an unresolved intermittent device hang at 832x832 with three workers (profiles/r02_pool_hang.txt);
 def test_pair_workers_on_one_gpu_give_the_single_worker_result(tmp_path):   # never seen at this size, but do not let it block a run
     """coarse_match.py:126-140 (n_workers Ray actors, ChainMap of their dicts) as host threads with one matcher + stream each on one GPU:
     bit-identical to the single worker, for the worker loop and for the whole stage."""
